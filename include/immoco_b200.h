@@ -1,0 +1,165 @@
+/*
+ * immoco_b200.h -- C ABI of the B200-native IM-MoCo hot path (libimmoco_b200.so).
+ *
+ * The reference (multimodallearning/MICCAI24_IMMoCo) is pure Python: it has no FFI layer of its
+ * own.  The seam it uses for this path is the tiny-cuda-nn torch binding plus ATen ops; every
+ * entry point below replaces one of those call sites (cited as file:line relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *    (the torch caching allocator in the shipped host code); the library allocates nothing;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises;
+ *  - return value: 0 on success, otherwise the cudaError_t of the failed launch, or
+ *    IMMOCO_ERR_* (negative) for rejected arguments;
+ *  - complex tensors are interleaved (re, im) fp32 pairs, row-major (H, W);
+ *  - "enc" feature planes are level-major: enc[level][point] = float2 (the 2 features of a level).
+ */
+#ifndef IMMOCO_B200_H_
+#define IMMOCO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMMOCO_MAX_LEVELS 16
+#define IMMOCO_ERR_BAD_ARG (-1)
+#define IMMOCO_ERR_UNSUPPORTED (-2)
+
+#define IMMOCO_ACT_NONE 0
+#define IMMOCO_ACT_RELU 1
+#define IMMOCO_ACT_TANH 2
+
+/* Multiresolution hash-grid description (tiny-cuda-nn "Grid"/"Hash" encoding configured at
+ * src/models/immoco.py:27-37; semantics restated in oracle/immoco_oracle.py:make_grid_levels). */
+typedef struct immoco_grid_desc {
+  int32_t n_dims;                           /* 2 (image INR) or 3 (motion INR)          */
+  int32_t n_levels;                         /* <= IMMOCO_MAX_LEVELS                      */
+  float scale[IMMOCO_MAX_LEVELS];           /* base * per_level_scale^l - 1              */
+  uint32_t resolution[IMMOCO_MAX_LEVELS];   /* ceil(scale) + 1                           */
+  uint32_t entries[IMMOCO_MAX_LEVELS];      /* rows of the level's table                 */
+  uint32_t offset[IMMOCO_MAX_LEVELS + 1];   /* first row of each level (prefix sums)     */
+  uint32_t hashed[IMMOCO_MAX_LEVELS];       /* 1: coherent-prime hash, 0: dense index    */
+} immoco_grid_desc;
+
+/* Column structure of the movement-group masks (src/utils/motion_utils.py:56-109 produces masks
+ * that are constant along rows): K[:,l] = static_w[l]*F(I)[:,l] + sum_m w_ml * F(I_m)[:,l].   */
+typedef struct immoco_lines {
+  int32_t n_groups;            /* M                                                     */
+  const int32_t* group_ofs;    /* device, M+1 prefix offsets into line_idx / line_w      */
+  const int32_t* line_idx;     /* device, column index l of every (group, line) pair     */
+  const float* line_w;         /* device, mask value of that column in that group        */
+  const float* static_w;       /* device, W floats: 1 - sum_m masks[m, :, l]             */
+  int32_t max_lines;           /* max lines of any one group (shared-memory sizing)      */
+} immoco_lines;
+
+/* ---- (1) hash-grid encoding: replaces the encoding half of tcnn.NetworkWithInputEncoding
+ *          (src/models/immoco.py:60-65, called at :84-87 and :93) -------------------------- */
+int immoco_hashgrid_fwd(const immoco_grid_desc* grid, const float* coords, const float* table,
+                        float* enc, int64_t n_points, void* stream);
+/* grad_table += scatter(d_enc)  (adjoint of the gather; K12 "kernel_grid_backward") */
+int immoco_hashgrid_bwd(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
+                        float* grad_table, int64_t n_points, void* stream);
+
+/* ---- (2) INR MLP: replaces the network half of tcnn.NetworkWithInputEncoding
+ *          (configs at src/models/immoco.py:11-25).  One hidden layer of `width` (64 or 256),
+ *          no biases, W1: width x 32, W2: 16 x width (rows >= 2 are padding).
+ *          out[n][2]; out_tanh applies the outer .tanh() of immoco.py:93. ------------------- */
+int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2, float* out,
+                   int64_t n_points, int32_t width, int32_t act, int32_t out_tanh, void* stream);
+/* d_out is the cotangent of the PRE-tanh output. d_enc is written; g_w1/g_w2 are accumulated. */
+int immoco_mlp_bwd(const float* enc, const float* w1, const float* w2, const float* d_out,
+                   float* d_enc, float* g_w1, float* g_w2, int64_t n_points, int32_t width,
+                   int32_t act, void* stream);
+/* element-wise helper for the autograd wrapper: d_pre = d_post * (1 - y^2) */
+int immoco_tanh_bwd(const float* y, const float* d_post, float* d_pre, int64_t n, void* stream);
+
+/* ---- (3) centred un-normalised 2-D FFT: replaces FFT/IFFT (src/utils/data_utils.py:29-34)
+ *          inverse=0: forward (exp(-i..)); inverse=1: conjugate transform, scaled by `scale`
+ *          (1/(H*W) gives IFFT, 1 gives the adjoint of FFT).  tw_h / tw_w: exp(-2 pi i t/N). -- */
+int immoco_fft2c(const float* in, float* out, float* tmp, int32_t batch, int32_t h, int32_t w,
+                 const float* tw_h, const float* tw_w, int32_t inverse, float scale, void* stream);
+
+/* ---- (4) motion forward model: replaces IMMoCo.forward's grid_sample + FFT + mask-combine
+ *          (src/models/immoco.py:91-111).  image (H,W) complex, disp (M,H,W,2) = tanh output,
+ *          ident (H,W,2) identity grid.  k_out (H,W) complex.  c_tmp (H,W) complex scratch. -- */
+int immoco_forward_model(const float* image, const float* disp, const float* ident,
+                         const immoco_lines* lines, const float* tw_h, const float* tw_w,
+                         float* c_tmp, float* k_out, int32_t h, int32_t w, void* stream);
+/* adjoint: d_k (H,W) complex cotangent of k_out -> d_image (accumulated, +=) and d_disp (M,H,W,2,
+ * written): cotangent of disp, or of the PRE-tanh motion-INR output when pre_tanh != 0
+ * (multiplied by 1 - disp^2, fusing the backward of the .tanh() at immoco.py:93). */
+int immoco_forward_model_bwd(const float* d_k, const float* image, const float* disp,
+                             const float* ident, const immoco_lines* lines, const float* tw_h,
+                             const float* tw_w, float* c_tmp, float* d_image, float* d_disp,
+                             int32_t pre_tanh, int32_t h, int32_t w, void* stream);
+
+/* ---- (5) fused column pass of the fit loop: K = colFFT(C); loss_acc[0] += sum|K-K_in|^2;
+ *          d_c = colFFT^H((K-K_in)/(H*W))  (F.mse_loss, src/models/immoco.py:170-171) ------- */
+int immoco_colpass_loss(const float* c, const float* k_in, float* k_out, float* d_c,
+                        double* loss_acc, const float* tw_h, int32_t h, int32_t w, void* stream);
+
+/* ---- (6) gradient-entropy prior (src/utils/losses.py:20-40): loss_acc[0] += GE(image);
+ *          d_image = grad_scale * dGE/dimage (written when accumulate==0, else +=) --------- */
+int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc, float* d_image,
+                        int32_t accumulate, int32_t h, int32_t w, void* stream);
+
+/* ---- (7) fused Adam (torch.optim.Adam defaults, src/models/immoco.py:149-154,166,175):
+ *          m,v,p updated in one pass, grad zeroed (optimizer.zero_grad fused). ------------- */
+int immoco_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     double lr, double beta1, double beta2, double eps, int32_t step,
+                     int32_t zero_grad, void* stream);
+
+/* ---- (8) composite: iterations [it_begin, it_end) of the optimisation loop
+ *          (src/models/immoco.py:164-181) on caller-provided buffers. ---------------------- */
+typedef struct immoco_fit {
+  int32_t h, w, m;                 /* image rows, phase-encode lines, movement groups        */
+  immoco_grid_desc grid_image;     /* 2-D */
+  immoco_grid_desc grid_motion;    /* 3-D */
+  int32_t width_image, act_image;  /* 256, ReLU */
+  int32_t width_motion, act_motion;/* 64, Tanh  */
+  /* flat parameter vector [motion (n_motion) | image (n_image)], each [W1 | W2 | table] */
+  int64_t n_motion, n_image;
+  float* params; float* grads; float* exp_avg; float* exp_avg_sq;
+  const float* coords_image;       /* (H*W, 2)  identity grid (x=col, y=row)                 */
+  const float* coords_motion;      /* (M*H*W,3) (m,row,col)                                  */
+  immoco_lines lines;
+  const float* tw_h; const float* tw_w;
+  const float* k_in;               /* (H,W) complex, normalised measured k-space             */
+  float* enc_image;  float* d_enc_image;    /* 16 x P x 2                                    */
+  float* enc_motion; float* d_enc_motion;   /* 16 x M*P x 2                                  */
+  float* image; float* d_image;             /* P x 2                                         */
+  float* disp;  float* d_disp;              /* M*P x 2                                       */
+  float* c_tmp; float* d_c; float* k_out;   /* P x 2 each                                    */
+  double* loss;                    /* 2 doubles per iteration: sum|dK|^2, GE (pre-zeroed)    */
+  double lr, beta1, beta2, eps;
+} immoco_fit;
+
+/* Optional per-kernel timing: events are recorded around every kernel of each iteration `it`
+ * with it % profile_every == profile_every - 1 (prof may be NULL).  Slot order:
+ * 0 hashgrid_fwd_image, 1 mlp_fwd_image, 2 hashgrid_fwd_motion, 3 mlp_fwd_motion, 4 fft_rows,
+ * 5 motion_rows_fwd, 6 colpass_loss, 7 grad_entropy, 8 fft_rows_adj, 9 motion_rows_bwd,
+ * 10 mlp_bwd_motion, 11 hashgrid_bwd_motion, 12 mlp_bwd_image, 13 hashgrid_bwd_image, 14 adam. */
+#define IMMOCO_PROFILE_SLOTS 15
+typedef struct immoco_profile immoco_profile;
+immoco_profile* immoco_profile_create(int32_t capacity);
+void immoco_profile_destroy(immoco_profile* prof);
+int immoco_profile_read(immoco_profile* prof, float* ms_sum);
+
+int immoco_fit_run(const immoco_fit* fit, int32_t it_begin, int32_t it_end,
+                   const float* lambdas_host, void* stream, immoco_profile* prof,
+                   int32_t profile_every);
+
+/* library/ABI version and the number of kernel launches one fit iteration issues */
+int immoco_abi_version(void);
+/* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit): lets a foreign-language
+ * binding assert that its struct mirrors match this build. */
+void immoco_struct_sizes(int32_t out[3]);
+int immoco_launches_per_iteration(int32_t m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMMOCO_B200_H_ */

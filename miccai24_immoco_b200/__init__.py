@@ -1,0 +1,25 @@
+"""B200-native IM-MoCo instance optimiser (hot path of multimodallearning/MICCAI24_IMMoCo).
+
+Public surface = the reference's own names for this path:
+  imcoco_motion_correction, IMMoCo, make_grids, network_config, mot_network_config,
+  encoding_config, ClearCache                        (src/models/immoco.py)
+  NetworkWithInputEncoding                           (tinycudann, as used at immoco.py:60-65)
+  FFT, IFFT                                          (src/utils/data_utils.py:29-34)
+  GradientEntropyLoss                                (src/utils/losses.py:20-40)
+  extract_movement_groups                            (src/utils/motion_utils.py:56-109)
+Every compute call goes to hand-written sm_100a kernels in libimmoco_b200.so through the C ABI of
+include/immoco_b200.h; there is no CPU or eager-PyTorch fallback.
+"""
+from ._native import build, lib, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
+from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_config,  # noqa: F401
+                     imcoco_motion_correction, lambda_schedule, make_grids, mot_network_config,
+                     network_config)
+from .motion_utils import extract_movement_groups, lines_from_mask  # noqa: F401
+from .ops import FFT, IFFT, GradientEntropyLoss, NetworkWithInputEncoding  # noqa: F401
+
+__all__ = [
+    "imcoco_motion_correction", "IMMoCo", "make_grids", "network_config", "mot_network_config",
+    "encoding_config", "ClearCache", "NetworkWithInputEncoding", "FFT", "IFFT",
+    "GradientEntropyLoss", "extract_movement_groups", "lines_from_mask", "FitEngine",
+    "LineStructure", "lambda_schedule", "build", "lib",
+]

@@ -1,0 +1,76 @@
+// Shared device helpers for the IM-MoCo sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "immoco_b200.h"
+
+#define IMMOCO_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized as multiples of this
+
+#define IMMOCO_LAUNCH_CHECK()                      \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// hash-grid index maths (tiny-cuda-nn grid.h grid_index / coherent-prime hash, restated in
+// oracle/immoco_oracle.py:grid_corner_index).  All arithmetic is uint32 and wraps.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__host__ __device__ __forceinline__ uint32_t grid_index(const uint32_t (&q)[D], uint32_t hashed,
+                                                        uint32_t entries, uint32_t res) {
+  uint32_t idx;
+  if (hashed) {
+    idx = q[0];  // prime 1
+    if (D > 1) idx ^= q[1] * 2654435761u;
+    if (D > 2) idx ^= q[2] * 805459861u;
+  } else {
+    uint32_t stride = 1;
+    idx = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      idx += q[d] * stride;
+      stride *= res;
+    }
+  }
+  // entries is a power of two for every level of the reference configuration; keep the general
+  // modulo for others (round-up-to-8 dense levels of odd resolutions).
+  return ((entries & (entries - 1)) == 0) ? (idx & (entries - 1)) : (idx % entries);
+}
+
+// pos = fmaf(scale, x, 0.5); cell = (uint32)(int)floor(pos); frac = pos - floor(pos)
+__host__ __device__ __forceinline__ void grid_pos(float x, float scale, uint32_t& cell, float& frac) {
+  float pos = fmaf(scale, x, 0.5f);
+  float fl = floorf(pos);
+  frac = pos - fl;
+  cell = (uint32_t)(int)fl;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == IMMOCO_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == IMMOCO_ACT_TANH) return tanhf(x);
+  return x;
+}
+// derivative expressed through the activation OUTPUT y
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  if (act == IMMOCO_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  if (act == IMMOCO_ACT_TANH) return 1.0f - y * y;
+  return 1.0f;
+}

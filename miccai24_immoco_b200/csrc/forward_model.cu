@@ -1,0 +1,559 @@
+// Motion forward model, its adjoint, the data-consistency loss and the gradient-entropy prior
+// (src/models/immoco.py:91-111,170-172; src/utils/data_utils.py:29-34;
+//  src/utils/losses.py:20-40).
+//
+// The movement-group masks are column indicators (src/utils/motion_utils.py:56-109), hence
+//   K[:,l] = F_H( w0[l] * F_W(I)[:,l] + sum_m w_m[l] * F_W(I_m)[:,l] )
+// so ONE full row pass (static image) + a pruned row DFT on the few lines of each group + ONE
+// column pass replace the reference's (M+1) full 2-D FFTs, and the resampled images I_m never
+// leave shared memory.  All transforms are centred and un-normalised.
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerCta = 4;   // row pass: transforms per CTA
+constexpr int kColsPerCta = 8;   // column pass: adjacent columns per CTA (64 B segments)
+
+__device__ __forceinline__ int wrap_mod(int a, int n) {
+  int r = a % n;
+  return r < 0 ? r + n : r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row pass: centred 1-D FFT along W of `rows` rows.
+//   out[r][l] (+)= scale * out_w[l] * sum_j in_w[j] * in[r][j] * exp(-/+ 2 pi i (l-W/2)(j-W/2)/W)
+// ------------------------------------------------------------------------------------------------
+template <bool INV>
+__global__ void __launch_bounds__(kThreads)
+fft_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int rows, int W,
+                const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
+                const float* __restrict__ in_w, const float* __restrict__ out_w, float scale,
+                int accumulate) {
+  extern __shared__ __align__(16) float2 sm2[];
+  float2* tw = sm2;
+  float2* a = tw + W;
+  float2* b = a + kRowsPerCta * W;
+  const int r0 = blockIdx.x * kRowsPerCta;
+  const int nr = min(kRowsPerCta, rows - r0);
+  const int half = W >> 1;
+  for (int t = threadIdx.x; t < W; t += kThreads) tw[t] = __ldg(tw_g + t);
+  for (int idx = threadIdx.x; idx < nr * W; idx += kThreads) {
+    const int r = idx / W, j = idx - r * W;
+    float2 v = __ldg(in + (size_t)(r0 + r) * W + j);
+    if (in_w) { const float s = __ldg(in_w + j); v.x *= s; v.y *= s; }
+    int jj = j + half; if (jj >= W) jj -= W;
+    a[r * W + jj] = v;
+  }
+  __syncthreads();
+  const float2* res = fft_smem<INV>(a, b, nr, W, plan, tw);
+  for (int idx = threadIdx.x; idx < nr * W; idx += kThreads) {
+    const int r = idx / W, l = idx - r * W;
+    int ll = l + half; if (ll >= W) ll -= W;
+    float2 v = res[r * W + ll];
+    float s = scale;
+    if (out_w) s *= __ldg(out_w + l);
+    v.x *= s; v.y *= s;
+    float2* o = out + (size_t)(r0 + r) * W + l;
+    if (accumulate) { const float2 p = *o; v.x += p.x; v.y += p.y; }
+    *o = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column pass helpers: a CTA owns kColsPerCta adjacent columns of one (H,W) image.
+// smem transform t = column, stride HP = H+1 (bank spread), input/output rolled by H/2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_cols(float2* a, const float2* __restrict__ in, int H, int W,
+                                          int l0, int nc, int HP) {
+  const int half = H >> 1;
+  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
+    const int i = idx / kColsPerCta, c = idx - i * kColsPerCta;
+    if (c < nc) {
+      int ii = i + half; if (ii >= H) ii -= H;
+      a[c * HP + ii] = __ldg(in + (size_t)i * W + l0 + c);
+    }
+  }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(kThreads)
+fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, int H, int W,
+                const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g, float scale) {
+  extern __shared__ __align__(16) float2 sm2[];
+  const int HP = H + 1;
+  float2* tw = sm2;
+  float2* a = tw + H;
+  float2* b = a + kColsPerCta * HP;
+  const int img = blockIdx.y;
+  const int l0 = blockIdx.x * kColsPerCta;
+  const int nc = min(kColsPerCta, W - l0);
+  const int half = H >> 1;
+  in += (size_t)img * H * W;
+  out += (size_t)img * H * W;
+  for (int t = threadIdx.x; t < H; t += kThreads) tw[t] = __ldg(tw_g + t);
+  load_cols(a, in, H, W, l0, nc, HP);
+  __syncthreads();
+  const float2* res = fft_smem<INV>(a, b, nc, HP, plan, tw);
+  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
+    const int k = idx / kColsPerCta, c = idx - k * kColsPerCta;
+    if (c < nc) {
+      int kk = k + half; if (kk >= H) kk -= H;
+      float2 v = res[c * HP + kk];
+      v.x *= scale; v.y *= scale;
+      out[(size_t)k * W + l0 + c] = v;
+    }
+  }
+}
+
+// Fused column pass of the fit loop:
+//   K = F_H(C);  loss += sum |K - K_in|^2;  dC = F_H^H((K - K_in) / (H W))
+__global__ void __launch_bounds__(kThreads)
+colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ k_in,
+                    float2* __restrict__ k_out, float2* __restrict__ d_c, double* __restrict__ loss_acc,
+                    int H, int W, const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) float2 sm2[];
+  __shared__ float red[kThreads / 32];
+  const int HP = H + 1;
+  float2* tw = sm2;
+  float2* a = tw + H;
+  float2* b = a + kColsPerCta * HP;
+  const int l0 = blockIdx.x * kColsPerCta;
+  const int nc = min(kColsPerCta, W - l0);
+  const int half = H >> 1;
+  for (int t = threadIdx.x; t < H; t += kThreads) tw[t] = __ldg(tw_g + t);
+  load_cols(a, c_in, H, W, l0, nc, HP);
+  __syncthreads();
+  float2* res = fft_smem<false>(a, b, nc, HP, plan, tw);
+  float2* other = (res == a) ? b : a;
+  const float inv_hw = 1.0f / ((float)H * (float)W);
+  float part = 0.0f;
+  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
+    const int k = idx / kColsPerCta, c = idx - k * kColsPerCta;
+    if (c < nc) {
+      int kk = k + half; if (kk >= H) kk -= H;
+      const float2 v = res[c * HP + kk];
+      const size_t g = (size_t)k * W + l0 + c;
+      const float2 t = __ldg(k_in + g);
+      k_out[g] = v;
+      const float dx = v.x - t.x, dy = v.y - t.y;
+      part = fmaf(dx, dx, part);
+      part = fmaf(dy, dy, part);
+      // cotangent goes back to the rolled slot it came from: input of the adjoint transform
+      res[c * HP + kk] = make_float2(dx * inv_hw, dy * inv_hw);
+    }
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int wv = 0; wv < kThreads / 32; ++wv) s += (double)red[wv];
+    atomicAdd(loss_acc, s);
+  }
+  const float2* adj = fft_smem<true>(res, other, nc, HP, plan, tw);
+  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
+    const int i = idx / kColsPerCta, c = idx - i * kColsPerCta;
+    if (c < nc) {
+      int ii = i + half; if (ii >= H) ii -= H;
+      d_c[(size_t)i * W + l0 + c] = adj[c * HP + ii];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear resampling geometry (ATen grid_sampler_2d, bilinear / zeros / align_corners=False,
+// called at src/models/immoco.py:97-107).
+// ------------------------------------------------------------------------------------------------
+struct Taps {
+  int x0, y0;
+  float wx0, wx1, wy0, wy1;   // (x1-ix), (ix-x0), (y1-iy), (iy-y0)
+};
+
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W) {
+  const float ix = ((gx + 1.0f) * (float)W - 1.0f) / 2.0f;
+  const float iy = ((gy + 1.0f) * (float)H - 1.0f) / 2.0f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  Taps t;
+  // clamp before the int cast: far-out samples (all taps out of range) stay out of range
+  t.x0 = (int)fminf(fmaxf(fx0, -2.0f), (float)W + 1.0f);
+  t.y0 = (int)fminf(fmaxf(fy0, -2.0f), (float)H + 1.0f);
+  t.wx1 = ix - fx0; t.wx0 = (fx0 + 1.0f) - ix;
+  t.wy1 = iy - fy0; t.wy0 = (fy0 + 1.0f) - iy;
+  return t;
+}
+
+__device__ __forceinline__ float2 fetch(const float2* __restrict__ img, int y, int x, int H, int W) {
+  if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) return __ldg(img + (size_t)y * W + x);
+  return make_float2(0.f, 0.f);
+}
+
+// One CTA per (row i, group m): resample row i of the image along group m's deformed grid into
+// shared memory, then evaluate the row DFT only at the group's phase-encode lines.
+__global__ void __launch_bounds__(kThreads)
+motion_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ disp,
+                       const float2* __restrict__ ident, const __grid_constant__ immoco_lines lines,
+                       const float2* __restrict__ tw_g, float2* __restrict__ c_out, int H, int W) {
+  extern __shared__ __align__(16) float2 sm2[];
+  float2* tw = sm2;
+  float2* row = tw + W;
+  const int i = blockIdx.x, m = blockIdx.y;
+  const int l_beg = __ldg(lines.group_ofs + m), l_end = __ldg(lines.group_ofs + m + 1);
+  if (l_beg == l_end) return;
+  for (int t = threadIdx.x; t < W; t += kThreads) tw[t] = __ldg(tw_g + t);
+  const size_t base = ((size_t)m * H + i) * W;
+  for (int j = threadIdx.x; j < W; j += kThreads) {
+    const float2 d = __ldg(disp + base + j);
+    const float2 id = __ldg(ident + (size_t)i * W + j);
+    const Taps t = make_taps(id.x + d.x, id.y + d.y, H, W);
+    const float2 nw = fetch(image, t.y0, t.x0, H, W), ne = fetch(image, t.y0, t.x0 + 1, H, W);
+    const float2 sw = fetch(image, t.y0 + 1, t.x0, H, W), se = fetch(image, t.y0 + 1, t.x0 + 1, H, W);
+    const float wnw = t.wx0 * t.wy0, wne = t.wx1 * t.wy0, wsw = t.wx0 * t.wy1, wse = t.wx1 * t.wy1;
+    row[j] = make_float2(nw.x * wnw + ne.x * wne + sw.x * wsw + se.x * wse,
+                         nw.y * wnw + ne.y * wne + sw.y * wsw + se.y * wse);
+  }
+  __syncthreads();
+  const int half = W >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int li = l_beg + warp; li < l_end; li += kThreads / 32) {
+    const int l = __ldg(lines.line_idx + li);
+    const int a = l - half;
+    float ax = 0.f, ay = 0.f;
+    for (int j = lane; j < W; j += 32) {
+      const float2 w = tw[wrap_mod(a * (j - half), W)];
+      const float2 v = row[j];
+      ax += v.x * w.x - v.y * w.y;
+      ay += v.x * w.y + v.y * w.x;
+    }
+    ax = warp_sum(ax);
+    ay = warp_sum(ay);
+    if (lane == 0) {
+      const float s = __ldg(lines.line_w + li);
+      atomicAdd(&c_out[(size_t)i * W + l].x, s * ax);
+      atomicAdd(&c_out[(size_t)i * W + l].y, s * ay);
+    }
+  }
+}
+
+// Adjoint of the kernel above: pruned inverse row DFT -> d(moved row) -> scatter into d_image
+// (grid_sampler_2d_backward) and the cotangent of the PRE-tanh displacement.
+__global__ void __launch_bounds__(kThreads)
+motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict__ image,
+                       const float2* __restrict__ disp, const float2* __restrict__ ident,
+                       const __grid_constant__ immoco_lines lines, const float2* __restrict__ tw_g,
+                       float2* __restrict__ d_image, float2* __restrict__ d_disp, int pre_tanh, int H,
+                       int W) {
+  extern __shared__ __align__(16) float2 sm2[];
+  float2* tw = sm2;
+  float2* gl = tw + W;
+  int* la = reinterpret_cast<int*>(gl + lines.max_lines);
+  const int i = blockIdx.x, m = blockIdx.y;
+  const int l_beg = __ldg(lines.group_ofs + m), l_end = __ldg(lines.group_ofs + m + 1);
+  const int nl = l_end - l_beg;
+  const int half = W >> 1;
+  for (int t = threadIdx.x; t < W; t += kThreads) tw[t] = __ldg(tw_g + t);
+  for (int li = threadIdx.x; li < nl; li += kThreads) {
+    const int l = __ldg(lines.line_idx + l_beg + li);
+    const float s = __ldg(lines.line_w + l_beg + li);
+    const float2 g = __ldg(d_c + (size_t)i * W + l);
+    gl[li] = make_float2(s * g.x, s * g.y);
+    la[li] = l - half;
+  }
+  __syncthreads();
+  const size_t base = ((size_t)m * H + i) * W;
+  const float mx = (float)W / 2.0f, my = (float)H / 2.0f;
+  for (int j = threadIdx.x; j < W; j += kThreads) {
+    const int bq = j - half;
+    float gr = 0.f, gi = 0.f;   // cotangent of the moved pixel (re, im)
+    for (int li = 0; li < nl; ++li) {
+      const float2 w = tw[wrap_mod(la[li] * bq, W)];
+      const float2 g = gl[li];
+      gr += g.x * w.x + g.y * w.y;     // g * conj(w)
+      gi += g.y * w.x - g.x * w.y;
+    }
+    const float2 d = __ldg(disp + base + j);
+    const float2 id = __ldg(ident + (size_t)i * W + j);
+    const Taps t = make_taps(id.x + d.x, id.y + d.y, H, W);
+    const int x0 = t.x0, y0 = t.y0, x1 = t.x0 + 1, y1 = t.y0 + 1;
+    const bool inx0 = (unsigned)x0 < (unsigned)W, inx1 = (unsigned)x1 < (unsigned)W;
+    const bool iny0 = (unsigned)y0 < (unsigned)H, iny1 = (unsigned)y1 < (unsigned)H;
+    float gix = 0.f, giy = 0.f;
+    if (iny0 && inx0) {
+      float2* p = d_image + (size_t)y0 * W + x0;
+      const float w = t.wx0 * t.wy0;
+      atomicAdd(p, make_float2(w * gr, w * gi));
+      const float2 v = __ldg(image + (size_t)y0 * W + x0);
+      const float dot = v.x * gr + v.y * gi;
+      gix -= dot * t.wy0; giy -= dot * t.wx0;
+    }
+    if (iny0 && inx1) {
+      float2* p = d_image + (size_t)y0 * W + x1;
+      const float w = t.wx1 * t.wy0;
+      atomicAdd(p, make_float2(w * gr, w * gi));
+      const float2 v = __ldg(image + (size_t)y0 * W + x1);
+      const float dot = v.x * gr + v.y * gi;
+      gix += dot * t.wy0; giy -= dot * t.wx1;
+    }
+    if (iny1 && inx0) {
+      float2* p = d_image + (size_t)y1 * W + x0;
+      const float w = t.wx0 * t.wy1;
+      atomicAdd(p, make_float2(w * gr, w * gi));
+      const float2 v = __ldg(image + (size_t)y1 * W + x0);
+      const float dot = v.x * gr + v.y * gi;
+      gix -= dot * t.wy1; giy += dot * t.wx0;
+    }
+    if (iny1 && inx1) {
+      float2* p = d_image + (size_t)y1 * W + x1;
+      const float w = t.wx1 * t.wy1;
+      atomicAdd(p, make_float2(w * gr, w * gi));
+      const float2 v = __ldg(image + (size_t)y1 * W + x1);
+      const float dot = v.x * gr + v.y * gi;
+      gix += dot * t.wy1; giy += dot * t.wx1;
+    }
+    const float sx = pre_tanh ? (1.0f - d.x * d.x) : 1.0f;
+    const float sy = pre_tanh ? (1.0f - d.y * d.y) : 1.0f;
+    d_disp[base + j] = make_float2(sx * (mx * gix), sy * (my * giy));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient entropy (src/utils/losses.py:20-40): GE = -sum G log(G + 1e-24),
+// G[i,j] = |I[i,j]-I[i,j+1]| [j<W-1] + |I[i,j]-I[i+1,j]| [i<H-1].  Value + gather-form gradient.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cabs2(float2 z) { return hypotf(z.x, z.y); }
+
+__device__ __forceinline__ float ge_dloss_dg(float g) {
+  const float ge = g + 1e-24f;
+  return -(logf(ge) + g / ge);
+}
+
+__global__ void __launch_bounds__(kThreads)
+grad_entropy_kernel(const float2* __restrict__ img, float grad_scale, double* __restrict__ loss_acc,
+                    float2* __restrict__ d_img, int accumulate, int H, int W) {
+  __shared__ float red[kThreads / 32];
+  const int P = H * W;
+  float part = 0.0f;
+  for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < P; idx += gridDim.x * kThreads) {
+    const int i = idx / W, j = idx - i * W;
+    const float2 z = __ldg(img + idx);
+    const bool has_r = j < W - 1, has_d = i < H - 1;
+    float2 gsum = make_float2(0.f, 0.f);
+    // own cell
+    float2 dx = make_float2(0.f, 0.f), dy = make_float2(0.f, 0.f);
+    if (has_r) { const float2 r = __ldg(img + idx + 1); dx = make_float2(z.x - r.x, z.y - r.y); }
+    if (has_d) { const float2 dn = __ldg(img + idx + W); dy = make_float2(z.x - dn.x, z.y - dn.y); }
+    const float ax = cabs2(dx), ay = cabs2(dy);
+    const float g = ax + ay;
+    part -= g * logf(g + 1e-24f);
+    const float gg = ge_dloss_dg(g);
+    if (ax > 0.f) { gsum.x += gg * dx.x / ax; gsum.y += gg * dx.y / ax; }
+    if (ay > 0.f) { gsum.x += gg * dy.x / ay; gsum.y += gg * dy.y / ay; }
+    // left neighbour's horizontal difference contains -z
+    if (j > 0) {
+      const float2 l = __ldg(img + idx - 1);
+      const float2 ldx = make_float2(l.x - z.x, l.y - z.y);
+      float2 ldy = make_float2(0.f, 0.f);
+      if (has_d) { const float2 ld = __ldg(img + idx - 1 + W); ldy = make_float2(l.x - ld.x, l.y - ld.y); }
+      const float lax = cabs2(ldx);
+      const float lg = lax + cabs2(ldy);
+      if (lax > 0.f) { const float s = ge_dloss_dg(lg) / lax; gsum.x -= s * ldx.x; gsum.y -= s * ldx.y; }
+    }
+    // upper neighbour's vertical difference contains -z
+    if (i > 0) {
+      const float2 u = __ldg(img + idx - W);
+      const float2 udy = make_float2(u.x - z.x, u.y - z.y);
+      float2 udx = make_float2(0.f, 0.f);
+      if (has_r) { const float2 ur = __ldg(img + idx - W + 1); udx = make_float2(u.x - ur.x, u.y - ur.y); }
+      const float uay = cabs2(udy);
+      const float ug = cabs2(udx) + uay;
+      if (uay > 0.f) { const float s = ge_dloss_dg(ug) / uay; gsum.x -= s * udy.x; gsum.y -= s * udy.y; }
+    }
+    float2 o = make_float2(grad_scale * gsum.x, grad_scale * gsum.y);
+    if (accumulate) { const float2 p = d_img[idx]; o.x += p.x; o.y += p.y; }
+    d_img[idx] = o;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int wv = 0; wv < kThreads / 32; ++wv) s += (double)red[wv];
+    atomicAdd(loss_acc, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------------
+struct Plans {
+  FftPlan h, w;
+  bool ok;
+};
+
+Plans make_plans(int H, int W) {
+  Plans p;
+  p.ok = (H >= 2) && (W >= 2) && (H % 2 == 0) && (W % 2 == 0) && fft_make_plan(H, &p.h) && fft_make_plan(W, &p.w);
+  return p;
+}
+
+template <typename K>
+void allow_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int launch_rows(const float* in, float* out, int rows, int W, const FftPlan& plan, const float* tw,
+                const float* in_w, const float* out_w, float scale, int accumulate, bool inv,
+                cudaStream_t s) {
+  const size_t smem = (size_t)(W + 2 * kRowsPerCta * W) * sizeof(float2);
+  if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
+  const int grid = (rows + kRowsPerCta - 1) / kRowsPerCta;
+  if (inv) {
+    allow_smem(fft_rows_kernel<true>, smem);
+    fft_rows_kernel<true><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, rows, W, plan,
+                                                      (const float2*)tw, in_w, out_w, scale, accumulate);
+  } else {
+    allow_smem(fft_rows_kernel<false>, smem);
+    fft_rows_kernel<false><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, rows, W, plan,
+                                                       (const float2*)tw, in_w, out_w, scale, accumulate);
+  }
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t cols_smem(int H) { return (size_t)(H + 2 * kColsPerCta * (H + 1)) * sizeof(float2); }
+
+int launch_cols(const float* in, float* out, int batch, int H, int W, const FftPlan& plan,
+                const float* tw, float scale, bool inv, cudaStream_t s) {
+  const size_t smem = cols_smem(H);
+  if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
+  dim3 grid((W + kColsPerCta - 1) / kColsPerCta, batch);
+  if (inv) {
+    allow_smem(fft_cols_kernel<true>, smem);
+    fft_cols_kernel<true><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, H, W, plan,
+                                                      (const float2*)tw, scale);
+  } else {
+    allow_smem(fft_cols_kernel<false>, smem);
+    fft_cols_kernel<false><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, H, W, plan,
+                                                       (const float2*)tw, scale);
+  }
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_motion_fwd(const float* image, const float* disp, const float* ident,
+                      const immoco_lines* lines, const float* tw_w, float* c_out, int H, int W,
+                      cudaStream_t s) {
+  if (lines->n_groups <= 0) return 0;
+  const size_t smem = (size_t)2 * W * sizeof(float2);
+  allow_smem(motion_rows_fwd_kernel, smem);
+  dim3 grid(H, lines->n_groups);
+  motion_rows_fwd_kernel<<<grid, kThreads, smem, s>>>((const float2*)image, (const float2*)disp,
+                                                     (const float2*)ident, *lines, (const float2*)tw_w,
+                                                     (float2*)c_out, H, W);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_motion_bwd(const float* d_c, const float* image, const float* disp, const float* ident,
+                      const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp,
+                      int pre_tanh, int H, int W, cudaStream_t s) {
+  if (lines->n_groups <= 0) return 0;
+  const size_t smem = (size_t)W * sizeof(float2) + (size_t)lines->max_lines * (sizeof(float2) + sizeof(int));
+  if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
+  allow_smem(motion_rows_bwd_kernel, smem);
+  dim3 grid(H, lines->n_groups);
+  motion_rows_bwd_kernel<<<grid, kThreads, smem, s>>>((const float2*)d_c, (const float2*)image,
+                                                     (const float2*)disp, (const float2*)ident, *lines,
+                                                     (const float2*)tw_w, (float2*)d_image,
+                                                     (float2*)d_disp, pre_tanh, H, W);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int immoco_fft2c(const float* in, float* out, float* tmp, int32_t batch, int32_t h,
+                            int32_t w, const float* tw_h, const float* tw_w, int32_t inverse,
+                            float scale, void* stream) {
+  if (batch < 0 || !in || !out || !tmp) return IMMOCO_ERR_BAD_ARG;
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  if (batch == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int e = launch_rows(in, tmp, batch * h, w, p.w, tw_w, nullptr, nullptr, 1.0f, 0, inverse != 0, s)) return e;
+  return launch_cols(tmp, out, batch, h, w, p.h, tw_h, scale, inverse != 0, s);
+}
+
+extern "C" int immoco_forward_model(const float* image, const float* disp, const float* ident,
+                                    const immoco_lines* lines, const float* tw_h, const float* tw_w,
+                                    float* c_tmp, float* k_out, int32_t h, int32_t w, void* stream) {
+  if (!lines) return IMMOCO_ERR_BAD_ARG;
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int e = launch_rows(image, c_tmp, h, w, p.w, tw_w, nullptr, lines->static_w, 1.0f, 0, false, s)) return e;
+  if (int e = launch_motion_fwd(image, disp, ident, lines, tw_w, c_tmp, h, w, s)) return e;
+  return launch_cols(c_tmp, k_out, 1, h, w, p.h, tw_h, 1.0f, false, s);
+}
+
+extern "C" int immoco_forward_model_bwd(const float* d_k, const float* image, const float* disp,
+                                        const float* ident, const immoco_lines* lines,
+                                        const float* tw_h, const float* tw_w, float* c_tmp,
+                                        float* d_image, float* d_disp, int32_t pre_tanh, int32_t h,
+                                        int32_t w, void* stream) {
+  if (!lines) return IMMOCO_ERR_BAD_ARG;
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int e = launch_cols(d_k, c_tmp, 1, h, w, p.h, tw_h, 1.0f, true, s)) return e;
+  if (int e = launch_rows(c_tmp, d_image, h, w, p.w, tw_w, lines->static_w, nullptr, 1.0f, 1, true, s)) return e;
+  return launch_motion_bwd(c_tmp, image, disp, ident, lines, tw_w, d_image, d_disp, pre_tanh, h, w, s);
+}
+
+extern "C" int immoco_colpass_loss(const float* c, const float* k_in, float* k_out, float* d_c,
+                                   double* loss_acc, const float* tw_h, int32_t h, int32_t w,
+                                   void* stream) {
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  const size_t smem = cols_smem(h);
+  if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
+  allow_smem(colpass_loss_kernel, smem);
+  const int grid = (w + kColsPerCta - 1) / kColsPerCta;
+  colpass_loss_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+      (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
+      (const float2*)tw_h);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc,
+                                   float* d_image, int32_t accumulate, int32_t h, int32_t w,
+                                   void* stream) {
+  if (h < 1 || w < 1) return IMMOCO_ERR_BAD_ARG;
+  const int P = h * w;
+  int grid = (P + kThreads - 1) / kThreads;
+  grad_entropy_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float2*)image, grad_scale,
+                                                                  loss_acc, (float2*)d_image,
+                                                                  accumulate, h, w);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+// used by fit.cu
+int immoco_rows_static(const float* in, float* out, int h, int w, const float* tw_w,
+                       const float* in_w, const float* out_w, int accumulate, bool inv, void* stream) {
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  return launch_rows(in, out, h, w, p.w, tw_w, in_w, out_w, 1.0f, accumulate, inv, (cudaStream_t)stream);
+}
+int immoco_motion_rows_fwd(const float* image, const float* disp, const float* ident,
+                           const immoco_lines* lines, const float* tw_w, float* c_out, int h, int w,
+                           void* stream) {
+  return launch_motion_fwd(image, disp, ident, lines, tw_w, c_out, h, w, (cudaStream_t)stream);
+}
+int immoco_motion_rows_bwd(const float* d_c, const float* image, const float* disp, const float* ident,
+                           const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp,
+                           int h, int w, void* stream) {
+  return launch_motion_bwd(d_c, image, disp, ident, lines, tw_w, d_image, d_disp, 1, h, w, (cudaStream_t)stream);
+}

@@ -1,0 +1,130 @@
+"""Hash-grid level table and parameter layout of the tcnn-style INRs.
+
+Follows the configuration the reference hands to tiny-cuda-nn (src/models/immoco.py:11-37) and
+tiny-cuda-nn's published Grid/Hash encoding rules (grid.h) as fixed by SURVEY.md Appendix B.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+OUT_PAD = 16          # tiny-cuda-nn pads the output layer to 16 rows
+N_ENCODED = 32        # kernels are specialised for 16 levels x 2 features
+
+_KNOWN_ENC_KEYS = {"otype", "type", "n_levels", "n_features_per_level", "log2_hashmap_size",
+                   "base_resolution", "per_level_scale", "interpolation", "fine_resolution"}
+_ACTS = {"none": nat.ACT_NONE, "relu": nat.ACT_RELU, "tanh": nat.ACT_TANH}
+
+
+@dataclass(frozen=True)
+class GridSpec:
+    n_dims: int
+    n_levels: int
+    scales: Tuple[float, ...]
+    resolutions: Tuple[int, ...]
+    entries: Tuple[int, ...]
+    offsets: Tuple[int, ...]
+    hashed: Tuple[int, ...]
+
+    @property
+    def n_rows(self) -> int:
+        return self.offsets[-1]
+
+    @property
+    def n_table_params(self) -> int:
+        return self.offsets[-1] * 2
+
+    def desc(self) -> nat.GridDesc:
+        d = nat.GridDesc()
+        d.n_dims = self.n_dims
+        d.n_levels = self.n_levels
+        for i in range(self.n_levels):
+            d.scale[i] = self.scales[i]
+            d.resolution[i] = self.resolutions[i]
+            d.entries[i] = self.entries[i]
+            d.hashed[i] = self.hashed[i]
+        for i in range(self.n_levels + 1):
+            d.offset[i] = self.offsets[i]
+        return d
+
+
+def grid_spec(n_dims: int, cfg: dict) -> GridSpec:
+    """Level scales / resolutions / entry counts / offsets of a Grid-Hash encoding."""
+    if n_dims not in (2, 3):
+        raise NotImplementedError("the IM-MoCo path uses 2-D and 3-D hash grids only")
+    if str(cfg.get("otype", "Grid")) not in ("Grid", "HashGrid") or str(cfg.get("type", "Hash")) != "Hash":
+        raise NotImplementedError("only the Grid/Hash encoding is implemented")
+    if str(cfg.get("interpolation", "Linear")) != "Linear":
+        raise NotImplementedError("only Linear interpolation is implemented")
+    n_levels = int(cfg.get("n_levels", 16))
+    n_feat = int(cfg.get("n_features_per_level", 2))
+    if n_levels != 16 or n_feat != 2:
+        raise NotImplementedError("kernels are specialised for n_levels=16, n_features_per_level=2")
+    log2_t = int(cfg.get("log2_hashmap_size", 19))
+    base = int(cfg.get("base_resolution", 16))
+    log2_pls = math.log2(float(cfg.get("per_level_scale", 2.0)))
+    scales, ress, ents, offs, hashed = [], [], [], [0], []
+    for lvl in range(n_levels):
+        scale = float(np.float32(np.exp2(np.float32(lvl * log2_pls)) * np.float32(base) - np.float32(1.0)))
+        res = int(math.ceil(scale)) + 1
+        dense = res ** n_dims
+        cap = 0xFFFFFFFF // 2
+        n = cap if float(dense) > float(cap) else dense
+        n = min((n + 7) // 8 * 8, 1 << log2_t)
+        # hash iff the dense index range walked by grid_index() exceeds the level's entry count
+        stride, dim = 1, 0
+        while dim < n_dims and stride <= n:
+            stride *= res
+            dim += 1
+        scales.append(scale)
+        ress.append(res)
+        ents.append(n)
+        offs.append(offs[-1] + n)
+        hashed.append(1 if n < stride else 0)
+    if offs[-1] >= 2 ** 31:
+        raise NotImplementedError("table too large")
+    return GridSpec(n_dims, n_levels, tuple(scales), tuple(ress), tuple(ents), tuple(offs), tuple(hashed))
+
+
+@dataclass(frozen=True)
+class MlpSpec:
+    width: int
+    act: int
+
+    @property
+    def n_w1(self) -> int:
+        return self.width * N_ENCODED
+
+    @property
+    def n_params(self) -> int:
+        return self.width * N_ENCODED + OUT_PAD * self.width
+
+
+def mlp_spec(cfg: dict) -> MlpSpec:
+    """Accepts both otype strings the reference uses (CutLassMLP / FullyFusedMLP)."""
+    otype = str(cfg.get("otype", "FullyFusedMLP")).lower()
+    if otype not in ("cutlassmlp", "fullyfusedmlp"):
+        raise NotImplementedError(f"network otype {cfg.get('otype')!r} is not on the IM-MoCo path")
+    width = int(cfg.get("n_neurons", 64))
+    if width not in (64, 256):
+        raise NotImplementedError("n_neurons must be 64 or 256")
+    if int(cfg.get("n_hidden_layers", 1)) != 1:
+        raise NotImplementedError("n_hidden_layers must be 1")
+    act = str(cfg.get("activation", "ReLU")).lower()
+    if act not in ("relu", "tanh"):
+        raise NotImplementedError("activation must be ReLU or Tanh")
+    if str(cfg.get("output_activation", "None")).lower() != "none":
+        raise NotImplementedError("output_activation must be None")
+    return MlpSpec(width, _ACTS[act])
+
+
+def twiddles(n: int) -> np.ndarray:
+    """exp(-2 pi i t / n), t = 0..n-1, evaluated in float64 and rounded once -> (n, 2) float32."""
+    t = np.arange(n, dtype=np.float64)
+    ang = -2.0 * np.pi * t / n
+    return np.stack([np.cos(ang), np.sin(ang)], axis=1).astype(np.float32)

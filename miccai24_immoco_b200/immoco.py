@@ -1,0 +1,352 @@
+"""IM-MoCo model and per-instance optimisation loop on the B200 CUDA path.
+
+Host-side mirror of the reference's src/models/immoco.py: same names, call signatures and
+argument meaning (``IMMoCo(masks)``, ``imcoco_motion_correction(kspace_corr, masks, iters,
+learning_rate, lambda_ge, debug)``, ``make_grids``, the three config dicts, ``ClearCache``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native as nat
+from .encoding import twiddles
+from .ops import (FFT, IFFT, GradientEntropyLoss, NetworkWithInputEncoding, _need_cuda, _stream,
+                  twiddle_table)
+
+# src/models/immoco.py:11-37 (same keys / values; passed straight to the INR constructor)
+network_config = {
+    "otype": "CutLassMLP",
+    "activation": "ReLU",
+    "output_activation": "None",
+    "n_neurons": 256,
+    "n_hidden_layers": 1,
+}
+
+mot_network_config = {
+    "otype": "FullyFusedMLP",
+    "activation": "Tanh",
+    "output_activation": "None",
+    "n_neurons": 64,
+    "n_hidden_layers": 1,
+}
+
+encoding_config = {
+    "otype": "Grid",
+    "type": "Hash",
+    "n_levels": 16,
+    "n_features_per_level": 2,
+    "log2_hashmap_size": 19,
+    "base_resolution": 16,
+    "fine_resolution": 320,
+    "per_level_scale": 2,
+    "interpolation": "Linear",
+}
+
+
+class ClearCache:
+    """Context manager of immoco.py:40-45."""
+
+    def __enter__(self):
+        torch.cuda.empty_cache()
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        torch.cuda.empty_cache()
+
+
+def make_grids(sizes, device="cpu"):
+    """(prod(sizes), len(sizes)) coordinates in [-1, 1], "ij" order (immoco.py:48-53).
+
+    The linspace values are produced on the CPU and copied, so they are bit-identical on every
+    device (the kernels read coordinates from memory, they do not regenerate them)."""
+    axes = [torch.linspace(-1, 1, int(s)) for s in sizes]
+    grid = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).view(-1, len(sizes))
+    return grid.to(device)
+
+
+def _identity_grid(h: int, w: int, device) -> torch.Tensor:
+    theta = torch.eye(2, 3).unsqueeze(0)
+    return F.affine_grid(theta, torch.Size((1, 1, h, w)), align_corners=True).to(device)
+
+
+class LineStructure:
+    """Column structure of (M, H, W) movement-group masks, uploaded once per instance.
+
+    The reference builds masks with extract_movement_groups (motion_utils.py:56-109): every mask
+    is constant along rows.  Masks that vary along rows are rejected (documented limitation)."""
+
+    def __init__(self, masks: torch.Tensor):
+        if masks.dim() != 3:
+            raise ValueError("masks must have shape (num_movements, H, num_lines)")
+        m, h, w = masks.shape
+        mf = masks.detach().to(torch.float32)
+        if m > 0 and h > 1 and not bool((mf == mf[:, :1, :]).all()):
+            raise NotImplementedError(
+                "movement-group masks must be constant along dim -2 (column indicators, as produced "
+                "by extract_movement_groups); row-varying masks are not supported by the CUDA path")
+        cols = mf[:, 0, :].cpu().numpy() if m > 0 else np.zeros((0, w), np.float32)   # (M, W)
+        ofs, idx, wt = [0], [], []
+        for g in range(m):
+            nz = np.nonzero(cols[g])[0]
+            idx.extend(int(v) for v in nz)
+            wt.extend(float(cols[g, v]) for v in nz)
+            ofs.append(len(idx))
+        static = (1.0 - cols.sum(0)).astype(np.float32) if m > 0 else np.ones(w, np.float32)
+        dev = masks.device
+        self.m, self.h, self.w = m, h, w
+        self.group_ofs = torch.tensor(ofs, dtype=torch.int32, device=dev)
+        self.line_idx = torch.tensor(idx if idx else [0], dtype=torch.int32, device=dev)
+        self.line_w = torch.tensor(wt if wt else [0.0], dtype=torch.float32, device=dev)
+        self.static_w = torch.from_numpy(static).to(dev)
+        self.max_lines = max([ofs[i + 1] - ofs[i] for i in range(m)] + [1])
+        self.n_lines = len(idx)
+
+    def struct(self) -> nat.Lines:
+        s = nat.Lines()
+        s.n_groups = self.m
+        s.group_ofs = self.group_ofs.data_ptr()
+        s.line_idx = self.line_idx.data_ptr()
+        s.line_w = self.line_w.data_ptr()
+        s.static_w = self.static_w.data_ptr()
+        s.max_lines = self.max_lines
+        return s
+
+
+class _ForwardModelFunction(torch.autograd.Function):
+    """k = F(I) * (1 - sum_m S_m) + sum_m F(warp_m(I)) * S_m   (immoco.py:91-111), one fused op."""
+
+    @staticmethod
+    def forward(ctx, image_ri, disp, model):
+        lib = nat.lib()
+        h, w = model.x, model.num_lines
+        image_ri = image_ri.detach().contiguous()
+        disp = disp.detach().contiguous()
+        dev = image_ri.device
+        c_tmp = torch.empty((h, w, 2), dtype=torch.float32, device=dev)
+        k = torch.empty((h, w, 2), dtype=torch.float32, device=dev)
+        lines = model._lines.struct()
+        nat.check(lib.immoco_forward_model(image_ri.data_ptr(), disp.data_ptr(), model._ident.data_ptr(),
+                                           C.byref(lines), twiddle_table(h, dev).data_ptr(),
+                                           twiddle_table(w, dev).data_ptr(), c_tmp.data_ptr(),
+                                           k.data_ptr(), h, w, _stream()), "forward_model")
+        ctx.save_for_backward(image_ri, disp)
+        ctx.model = model
+        return k
+
+    @staticmethod
+    def backward(ctx, d_k):
+        image_ri, disp = ctx.saved_tensors
+        model = ctx.model
+        lib = nat.lib()
+        h, w = model.x, model.num_lines
+        dev = image_ri.device
+        d_k = d_k.contiguous().float()
+        c_tmp = torch.empty((h, w, 2), dtype=torch.float32, device=dev)
+        d_image = torch.zeros_like(image_ri)
+        d_disp = torch.zeros_like(disp)
+        lines = model._lines.struct()
+        nat.check(lib.immoco_forward_model_bwd(d_k.data_ptr(), image_ri.data_ptr(), disp.data_ptr(),
+                                               model._ident.data_ptr(), C.byref(lines),
+                                               twiddle_table(h, dev).data_ptr(),
+                                               twiddle_table(w, dev).data_ptr(), c_tmp.data_ptr(),
+                                               d_image.data_ptr(), d_disp.data_ptr(), 0, h, w, _stream()),
+                  "forward_model_bwd")
+        return d_image, d_disp, None
+
+
+class IMMoCo(nn.Module):
+    """Image INR + Motion INR + motion forward model (immoco.py:56-113).
+
+    Attributes kept from the reference: image_inr, motion_inr, masks, num_movements, x, num_lines,
+    device, identy_grid, input_grid.  ``forward() -> (kspace_out, image_prior)``."""
+
+    def __init__(self, masks, image_seed: int = 1337, motion_seed: int = 1338):
+        super().__init__()
+        _need_cuda(masks, "IMMoCo(masks)")
+        dev = masks.device
+        with torch.cuda.device(dev):
+            self.image_inr = NetworkWithInputEncoding(2, 2, encoding_config, network_config,
+                                                      seed=image_seed, device=dev)
+            self.motion_inr = NetworkWithInputEncoding(3, 2, encoding_config, mot_network_config,
+                                                       seed=motion_seed, device=dev)
+        self.masks = masks
+        self.num_movements, self.x, self.num_lines = masks.shape
+        self.device = dev
+        self.identy_grid = _identity_grid(self.x, self.num_lines, dev)
+        self.input_grid = make_grids((self.num_movements, self.x, self.num_lines), device=dev)
+        self._lines = LineStructure(masks)
+        self._ident = self.identy_grid.view(-1, 2).contiguous()
+
+    def forward(self):
+        h, w, m = self.x, self.num_lines, self.num_movements
+        out = self.image_inr(self._ident).float().view(h, w, 2)
+        image_prior = torch.view_as_complex(out.contiguous())
+        if m > 0:
+            disp = self.motion_inr(self.input_grid).float().tanh().view(m, h, w, 2)
+        else:   # undefined in the reference: static branch only
+            disp = torch.zeros((0, h, w, 2), dtype=torch.float32, device=self.device)
+        k = _ForwardModelFunction.apply(out, disp, self)
+        return torch.view_as_complex(k), image_prior
+
+
+def lambda_schedule(iters: int, lambda_ge: float, variant: str = "main") -> List[float]:
+    """lambda used by each iteration.  main: immoco.py:180-181 (halved on every iteration that is
+    NOT a multiple of iters//10 after the midpoint; iters < 10 raises
+    ZeroDivisionError like the reference).  downstream: test_immoco_downstream.py:189-190."""
+    lams, lam = [], float(lambda_ge)
+    for j in range(iters):
+        lams.append(lam)
+        if variant == "main":
+            if j % (iters // 10) and j > (iters // 2):
+                lam *= 0.5
+        elif variant == "downstream":
+            if j % 10 == 0 and j > 80:
+                lam *= 0.5
+        else:
+            raise ValueError(f"unknown schedule variant {variant!r}")
+    return lams
+
+
+class FitEngine:
+    """Device state + native loop for ONE slice: both INRs' parameters, gradients and Adam moments
+    live in one flat fp32 vector [motion | image]; every iteration is 15 kernel launches issued by
+    ``immoco_fit_run`` with no host synchronisation."""
+
+    def __init__(self, model: IMMoCo, max_iters: int):
+        self.model = model
+        dev = model.device
+        h, w, m = model.x, model.num_lines, model.num_movements
+        p, mp = h * w, h * w * m
+        img, mot = model.image_inr, model.motion_inr
+        self.n_motion, self.n_image = mot.n_params, img.n_params
+        n = self.n_motion + self.n_image
+        self.params = torch.empty(n, dtype=torch.float32, device=dev)
+        self.params[: self.n_motion].copy_(mot.params.detach())
+        self.params[self.n_motion:].copy_(img.params.detach())
+        self.state = torch.zeros((3, n), dtype=torch.float32, device=dev)   # grads, exp_avg, exp_avg_sq
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.enc_image = torch.empty((16, p, 2), **f32)
+        self.d_enc_image = torch.empty((16, p, 2), **f32)
+        self.enc_motion = torch.empty((16, max(mp, 1), 2), **f32)
+        self.d_enc_motion = torch.empty((16, max(mp, 1), 2), **f32)
+        self.image = torch.zeros((h, w, 2), **f32)
+        self.d_image = torch.zeros((h, w, 2), **f32)
+        self.disp = torch.zeros((max(m, 1), h, w, 2), **f32)
+        self.d_disp = torch.zeros((max(m, 1), h, w, 2), **f32)
+        self.c_tmp = torch.empty((h, w, 2), **f32)
+        self.d_c = torch.empty((h, w, 2), **f32)
+        self.k_out = torch.zeros((h, w, 2), **f32)
+        self.k_in = torch.zeros((h, w, 2), **f32)
+        self.max_iters = max_iters
+        self.loss = torch.zeros((max_iters, 2), dtype=torch.float64, device=dev)
+        self.tw_h = twiddle_table(h, dev)
+        self.tw_w = twiddle_table(w, dev)
+        self.coords_motion = model.input_grid.contiguous() if m > 0 else torch.zeros((1, 3), **f32)
+        f = nat.Fit()
+        f.h, f.w, f.m = h, w, m
+        f.grid_image, f.grid_motion = img.grid.desc(), mot.grid.desc()
+        f.width_image, f.act_image = img.mlp.width, img.mlp.act
+        f.width_motion, f.act_motion = mot.mlp.width, mot.mlp.act
+        f.n_motion, f.n_image = self.n_motion, self.n_image
+        f.params = self.params.data_ptr()
+        f.grads = self.state[0].data_ptr()
+        f.exp_avg = self.state[1].data_ptr()
+        f.exp_avg_sq = self.state[2].data_ptr()
+        f.coords_image = model._ident.data_ptr()
+        f.coords_motion = self.coords_motion.data_ptr()
+        f.lines = model._lines.struct()
+        f.tw_h, f.tw_w = self.tw_h.data_ptr(), self.tw_w.data_ptr()
+        f.k_in = self.k_in.data_ptr()
+        f.enc_image, f.d_enc_image = self.enc_image.data_ptr(), self.d_enc_image.data_ptr()
+        f.enc_motion, f.d_enc_motion = self.enc_motion.data_ptr(), self.d_enc_motion.data_ptr()
+        f.image, f.d_image = self.image.data_ptr(), self.d_image.data_ptr()
+        f.disp, f.d_disp = self.disp.data_ptr(), self.d_disp.data_ptr()
+        f.c_tmp, f.d_c, f.k_out = self.c_tmp.data_ptr(), self.d_c.data_ptr(), self.k_out.data_ptr()
+        f.loss = self.loss.data_ptr()
+        f.lr, f.beta1, f.beta2, f.eps = 1e-2, 0.9, 0.999, 1e-8
+        self.fit = f
+        self.launches = 0
+
+    def set_kspace(self, k_in: torch.Tensor) -> None:
+        self.k_in.copy_(torch.view_as_real(k_in.to(torch.complex64)))
+
+    def reset(self, image_params: torch.Tensor, motion_params: torch.Tensor) -> None:
+        """Fresh instance: initial INR parameters, zero gradients / Adam moments / loss trace."""
+        self.params[: self.n_motion].copy_(motion_params)
+        self.params[self.n_motion:].copy_(image_params)
+        self.state.zero_()
+        self.loss.zero_()
+
+    def run(self, lambdas: List[float], learning_rate: float, it_begin: int = 0,
+            it_end: Optional[int] = None, profile=None, profile_every: int = 0) -> None:
+        it_end = len(lambdas) if it_end is None else it_end
+        if it_end > self.max_iters:
+            raise ValueError("more iterations than the loss buffer holds")
+        self.fit.lr = float(learning_rate)
+        lam = (C.c_float * len(lambdas))(*[float(v) for v in lambdas])
+        nat.check(nat.lib().immoco_fit_run(C.byref(self.fit), it_begin, it_end, lam, _stream(),
+                                           profile, profile_every), "fit_run")
+        self.launches += (it_end - it_begin) * nat.lib().immoco_launches_per_iteration(self.fit.m)
+
+    def loss_trace(self, lambdas: List[float]) -> np.ndarray:
+        """fp32 loss of every iteration: mse + fp32(lambda) * GE, assembled like the reference
+        (F.mse_loss mean over 2HW reals; GE.mul(lambda_ge) with a python-float lambda)."""
+        acc = self.loss[: len(lambdas)].cpu().numpy()
+        n = 2.0 * self.fit.h * self.fit.w
+        dc = (acc[:, 0] / n).astype(np.float32)
+        ge = acc[:, 1].astype(np.float32)
+        lam = np.asarray(lambdas, dtype=np.float64).astype(np.float32)
+        return dc + lam * ge
+
+    def write_back(self) -> None:
+        with torch.no_grad():
+            self.model.motion_inr.params.copy_(self.params[: self.n_motion])
+            self.model.image_inr.params.copy_(self.params[self.n_motion:])
+
+
+def imcoco_motion_correction(kspace_corr, masks, iters=200, learning_rate=1e-2, lambda_ge=1e-2,
+                             debug=False, *, image_params=None, motion_params=None,
+                             kmax: float = 16000.0, variant: str = "main", return_trace: bool = False):
+    """Fit Image INR + Motion INR to one motion-corrupted k-space (immoco.py:116-206).
+
+    Positional signature and defaults are the reference's.  Returns ``(image_prior,
+    kspace_foward_model)`` of the LAST iteration's forward pass, i.e. before the last Adam step
+    (SURVEY Q4), as detached complex64 CUDA tensors in the 16000-normalised scale (Q5).
+    Keyword-only extras: injected initial parameters (tests), ``kmax``/``variant`` for the
+    downstream copy's constants (test_immoco_downstream.py:152,189), ``return_trace``.
+    """
+    if not torch.cuda.is_available():
+        raise RuntimeError("imcoco_motion_correction needs a CUDA device (no CPU fallback)")
+    masks = masks.cuda()
+    model = IMMoCo(masks)
+    with torch.no_grad():
+        if image_params is not None:
+            model.image_inr.params.copy_(image_params.to(model.device))
+        if motion_params is not None:
+            model.motion_inr.params.copy_(motion_params.to(model.device))
+    kspace_corr = kspace_corr.to(model.device)
+    scale = kspace_corr.abs().max()
+    kspace_input = kspace_corr.div(scale).mul(kmax).clone().detach()
+    if debug:
+        print(f"Scale: {scale:.4f}")
+        print(f"Kspace input: {kspace_input.abs().min().item():.4f}, {kspace_input.abs().max().item():.4f}")
+    lambdas = lambda_schedule(iters, lambda_ge, variant)
+    engine = FitEngine(model, max(iters, 1))
+    engine.set_kspace(kspace_input)
+    engine.run(lambdas, learning_rate)
+    image_prior = torch.view_as_complex(engine.image.clone())
+    kspace_foward_model = torch.view_as_complex(engine.k_out.clone())
+    trace = engine.loss_trace(lambdas) if (return_trace or debug) else None
+    if debug:
+        for j in range(0, iters, 20):
+            print(f"iter: {j}, DC_Loss: {trace[j]:.4f}")
+    del engine, model
+    torch.cuda.empty_cache()
+    if return_trace:
+        return image_prior, kspace_foward_model, trace
+    return image_prior, kspace_foward_model

@@ -1,0 +1,251 @@
+"""ORACLE tooling -- pins oracle/immoco_oracle.py against the reference's OWN Python files and
+writes the golden vectors under tests/golden/.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py [--full] [--full-iters N]
+
+What it does
+* imports the reference's ``models/immoco.py``, ``utils/losses.py``, ``utils/data_utils.py``,
+  ``utils/motion_utils.py`` UNCHANGED from /root/reference/src, with stand-ins for the imports
+  that are absent here (h5py, matplotlib, IPython: never executed on this path; tinycudann:
+  replaced by the oracle's torch fp32 ``NetworkWithInputEncoding``, the "parity unpinned" seam);
+* asserts the oracle restatement reproduces the reference bit-for-bit on seeded inputs
+  (FFT/IFFT, gradient entropy, movement groups, motion simulation, IMMoCo.forward,
+  imcoco_motion_correction loss trace + returned tensors);
+* stores the reference-produced outputs as small fixtures (tests/golden/*.npz).
+
+Nothing here is imported by the product.  The GPU box never runs this file.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+REF = "/root/reference/src"
+
+from oracle import immoco_oracle as orc  # noqa: E402
+
+_INJECT = []  # queue of params handed to the next stand-in INR constructions
+
+
+def _install_stubs():
+    for name in ("h5py", "matplotlib", "matplotlib.pyplot", "IPython", "IPython.display"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["IPython.display"].clear_output = lambda *a, **k: None
+    sys.modules["IPython.display"].display = lambda *a, **k: None
+    tcnn = types.ModuleType("tinycudann")
+
+    def factory(n_in, n_out, enc, net):
+        mod = orc.NetworkWithInputEncoding(n_in, n_out, enc, net)
+        if _INJECT:
+            mod.params.data.copy_(_INJECT.pop(0))
+        return mod
+
+    tcnn.NetworkWithInputEncoding = factory
+    sys.modules["tinycudann"] = tcnn
+    torch.Tensor.cuda = lambda self, *a, **k: self  # CPU container: .cuda() is a no-op
+
+
+def _import_reference():
+    _install_stubs()
+    sys.path.insert(0, REF)
+    import models.immoco as ref_immoco
+    import utils.data_utils as ref_data
+    import utils.losses as ref_losses
+    import utils.motion_utils as ref_motion
+    return ref_immoco, ref_data, ref_losses, ref_motion
+
+
+def seeded_params(n_dims, net_cfg, seed):
+    lv = orc.make_grid_levels(n_dims, orc.ENCODING_CONFIG)
+    return orc.init_params(lv, net_cfg, seed)
+
+
+def eq(a, b, what):
+    if not torch.equal(a, b):
+        d = (a - b).abs().max().item()
+        raise AssertionError(f"oracle != reference for {what}: max abs diff {d}")
+    print(f"  pinned: {what}")
+
+
+def small_goldens(ref_immoco, ref_data, ref_losses, ref_motion, out_dir):
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    # --- centred FFT / IFFT, sizes used by the configs + odd factor 23 --------------------------
+    for (h, w) in ((32, 32), (48, 20), (64, 46)):
+        x = torch.complex(torch.randn(h, w, generator=g), torch.randn(h, w, generator=g))
+        eq(orc.FFT(x), ref_data.FFT(x), f"FFT {h}x{w}")
+        eq(orc.IFFT(x), ref_data.IFFT(x), f"IFFT {h}x{w}")
+        out[f"fft_in_{h}x{w}"] = x.numpy()
+        out[f"fft_out_{h}x{w}"] = ref_data.FFT(x).numpy()
+    # --- gradient entropy, value and gradient ----------------------------------------------------
+    x = torch.complex(torch.randn(24, 40, generator=g), torch.randn(24, 40, generator=g))
+    x[3, 4] = x[3, 5]          # exact zero difference -> sub-gradient 0 branch
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    la = orc.gradient_entropy(xa)
+    lb = ref_losses.GradientEntropyLoss()(xb)
+    la.backward()
+    lb.backward()
+    eq(la.detach(), lb.detach(), "gradient entropy value")
+    eq(xa.grad, xb.grad, "gradient entropy grad")
+    out["ge_in"] = x.numpy()
+    out["ge_val"] = lb.detach().numpy()
+    out["ge_grad"] = xb.grad.numpy()
+    # --- movement groups ----------------------------------------------------------------------------
+    pats = {
+        "empty": torch.zeros(16, dtype=torch.bool),
+        "all": torch.ones(16, dtype=torch.bool),
+        "runs": torch.tensor([0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0], dtype=torch.bool),
+        "edges": torch.tensor([1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1], dtype=torch.bool),
+        "single_last": torch.tensor([0] * 15 + [1], dtype=torch.bool),
+    }
+    for name, p in pats.items():
+        for ml in (False, True):
+            a = orc.extract_movement_groups(p, make_list=ml)
+            b = ref_motion.extract_movement_groups(p, make_list=ml)
+            if not (a.shape == b.shape and torch.equal(a, b)):
+                raise AssertionError(f"groups {name} make_list={ml}: {a.shape} vs {b.shape}")
+            out[f"groups_{name}_{int(ml)}"] = b.numpy()
+        out[f"groups_{name}_in"] = p.numpy()
+        print(f"  pinned: extract_movement_groups[{name}]")
+    # --- motion simulation (global RNG order) ----------------------------------------------------
+    img = orc.make_phantom(40, 40, seed=3)
+    torch.manual_seed(11)
+    ra = ref_motion.motion_simulation2D(img.clone(), 3)
+    torch.manual_seed(11)
+    oa = orc.motion_simulation2D(img.clone(), 3)
+    for i, nm in enumerate(("kspace", "mask", "rot", "trans")):
+        eq(oa[i], ra[i], f"motion_simulation2D.{nm}")
+    out["sim_image"] = img.numpy()
+    out["sim_kspace"] = ra[0].numpy()
+    out["sim_mask"] = ra[1].numpy()
+    out["sim_rot"] = ra[2].numpy()
+    out["sim_trans"] = ra[3].numpy()
+    np.savez_compressed(os.path.join(out_dir, "ops_small.npz"), **out)
+
+
+def _fft_via_fp64(x):
+    """Mathematically identical centred FFT evaluated in complex128 and rounded once: the
+    smallest possible 'different rounding' perturbation, used to measure how fast two exact
+    restatements of the loop drift apart (the tolerance band of the GPU parity tests)."""
+    return _ORIG_FFT(x.to(torch.complex128)).to(torch.complex64)
+
+
+_ORIG_FFT = orc.FFT
+
+
+def loop_golden(ref_immoco, tag, h, n_mov, seed, iters, out_dir, check_restatement=True,
+                small_payload=False):
+    """Reference loop (immoco.py:116-206) with injected params on a synthetic square slice."""
+    case = orc.make_case(h, h, n_mov, seed)
+    masks = case["masks"]
+    p_img = seeded_params(2, orc.IMAGE_NETWORK_CONFIG, 100 + seed)
+    p_mot = seeded_params(3, orc.MOTION_NETWORK_CONFIG, 200 + seed)
+    # forward only, reference class
+    _INJECT[:] = [p_img.clone(), p_mot.clone()]       # image_inr is built first (immoco.py:60-65)
+    ref_model = ref_immoco.IMMoCo(masks)
+    with torch.no_grad():
+        k_ref, im_ref = ref_model()
+    if check_restatement:
+        o_model = orc.IMMoCo(masks, image_params=p_img, motion_params=p_mot)
+        with torch.no_grad():
+            k_o, im_o = o_model()
+        eq(k_o, k_ref, f"{tag}: IMMoCo.forward k-space")
+        eq(im_o, im_ref, f"{tag}: IMMoCo.forward image")
+    # loop: the reference keeps no loss trace unless debug (which needs matplotlib) -> capture
+    # the loss through the GradientEntropyLoss/mse call chain by wrapping Tensor.backward.
+    trace = []
+    orig_backward = torch.Tensor.backward
+
+    def spy(self, *a, **k):
+        trace.append(float(self.detach()))
+        return orig_backward(self, *a, **k)
+
+    torch.Tensor.backward = spy
+    _INJECT[:] = [p_img.clone(), p_mot.clone()]
+    t0 = time.time()
+    try:
+        im_fin, k_fin = ref_immoco.imcoco_motion_correction(
+            case["kspace_motion"], masks, iters=iters, learning_rate=1e-2, lambda_ge=1e-2, debug=False)
+    finally:
+        torch.Tensor.backward = orig_backward
+    print(f"  {tag}: reference loop {iters} its in {time.time() - t0:.1f}s; loss {trace[0]:.6g} -> {trace[-1]:.6g}")
+    if check_restatement:
+        im_o, k_o, tr_o = orc.imcoco_motion_correction(
+            case["kspace_motion"], masks, iters=iters, image_params=p_img, motion_params=p_mot,
+            return_trace=True)
+        if tr_o != trace:
+            bad = [i for i, (a, b) in enumerate(zip(tr_o, trace)) if a != b]
+            raise AssertionError(f"{tag}: loss trace differs first at it {bad[0]}: {tr_o[bad[0]]} vs {trace[bad[0]]}")
+        eq(im_o.detach(), im_fin.detach(), f"{tag}: loop final image")
+        eq(k_o.detach(), k_fin.detach(), f"{tag}: loop final k-space")
+    gt = case["image"].abs()
+    met_in = orc.crop_metrics(orc.IFFT(case["kspace_motion"]).abs(), gt)
+    met_out = orc.crop_metrics(im_fin.detach().abs(), gt)
+    print(f"  {tag}: corrupted {met_in} -> corrected {met_out}")
+    # drift band: the oracle loop with an fp64-evaluated FFT (same maths, other rounding)
+    orc.FFT = _fft_via_fp64
+    try:
+        im_p, _, tr_p = orc.imcoco_motion_correction(
+            case["kspace_motion"], masks, iters=iters, image_params=p_img, motion_params=p_mot,
+            return_trace=True)
+    finally:
+        orc.FFT = _ORIG_FFT
+    met_p = orc.crop_metrics(im_p.detach().abs(), gt)
+    rel = [abs(a - b) / abs(a) for a, b in zip(trace, tr_p)]
+    print(f"  {tag}: rounding-drift band: max rel loss diff its<10 {max(rel[:10]):.2e}, "
+          f"<{min(50, iters)} {max(rel[:50]):.2e}, all {max(rel):.2e}; perturbed metrics {met_p}")
+    payload = dict(
+        h=h, n_mov=n_mov, seed=seed, iters=iters,
+        masks_lines=masks[:, 0, :].numpy().astype(np.uint8),
+        k_fwd0=k_ref.numpy(),
+        loss_trace=np.asarray(trace, dtype=np.float64),
+        loss_trace_perturbed=np.asarray(tr_p, dtype=np.float64),
+        image_final=im_fin.detach().numpy(),
+        psnr_in=met_in["psnr"], ssim_in=met_in["ssim"],
+        psnr_out=met_out["psnr"], ssim_out=met_out["ssim"],
+        psnr_out_perturbed=met_p["psnr"], ssim_out_perturbed=met_p["ssim"])
+    if not small_payload:
+        payload.update(kspace_motion=case["kspace_motion"].numpy(), image0=im_ref.numpy(),
+                       k_final=k_fin.detach().numpy())
+    np.savez_compressed(os.path.join(out_dir, f"loop_{tag}.npz"), **payload)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also the 320x320, n_M=4 case (slow)")
+    ap.add_argument("--full-iters", type=int, default=200)
+    ap.add_argument("--skip-small", action="store_true")
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count() or 1)
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    ref_immoco, ref_data, ref_losses, ref_motion = _import_reference()
+    if not args.skip_small:
+        print("[ops]")
+        small_goldens(ref_immoco, ref_data, ref_losses, ref_motion, out_dir)
+        print("[loop 64x64, n_M=2, 30 its]")
+        loop_golden(ref_immoco, "s64_m2", 64, 2, seed=5, iters=30, out_dir=out_dir)
+        print("[loop 32x32, n_M=1, 20 its]")
+        loop_golden(ref_immoco, "s32_m1", 32, 1, seed=6, iters=20, out_dir=out_dir)
+    if args.full:
+        print(f"[loop 320x320, n_M=4, {args.full_iters} its]")
+        loop_golden(ref_immoco, f"c2_i{args.full_iters}", 320, 4, seed=1000, iters=args.full_iters,
+                    out_dir=out_dir, check_restatement=False, small_payload=True)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

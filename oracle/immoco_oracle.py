@@ -1,0 +1,687 @@
+"""ORACLE -- test infrastructure, NOT product code.
+
+A plain torch (fp32, device-agnostic, CPU by default) restatement of the IM-MoCo
+per-instance optimisation path of multimodallearning/MICCAI24_IMMoCo.  It is the
+checker for the CUDA path in ``miccai24_immoco_b200``: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import it.  Nothing in the product package imports this module.
+
+Pinning status
+--------------
+* Everything that lives in the reference repository itself (centred FFT, gradient
+  entropy, forward model, optimisation loop, lambda schedule, movement groups,
+  motion simulation) is PINNED: ``oracle/gen_golden.py`` imports the reference's own
+  files from /root/reference (with stand-ins for absent third-party imports) and
+  checks this restatement against them bit-for-bit, then writes ``tests/golden``.
+* The hash-grid encoding + MLP arithmetic lives in tiny-cuda-nn (un-vendored,
+  un-pinned: README.md:56-60 installs GitHub HEAD) -> **parity unpinned** at that
+  boundary.  The restatement below follows tiny-cuda-nn's published algorithm
+  (grid.h: grid_scale / grid_resolution / grid_index / coherent-prime hash, linear
+  interpolation, params = [network | encoding]) in fp32.
+* SSIM follows piq 0.8.0's published algorithm (absent here) -> parity unpinned.
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------
+# configs  (src/models/immoco.py:11-37)
+# ----------------------------------------------------------------------------------------------
+IMAGE_NETWORK_CONFIG = {
+    "otype": "CutLassMLP",
+    "activation": "ReLU",
+    "output_activation": "None",
+    "n_neurons": 256,
+    "n_hidden_layers": 1,
+}
+MOTION_NETWORK_CONFIG = {
+    "otype": "FullyFusedMLP",
+    "activation": "Tanh",
+    "output_activation": "None",
+    "n_neurons": 64,
+    "n_hidden_layers": 1,
+}
+ENCODING_CONFIG = {
+    "otype": "Grid",
+    "type": "Hash",
+    "n_levels": 16,
+    "n_features_per_level": 2,
+    "log2_hashmap_size": 19,
+    "base_resolution": 16,
+    "fine_resolution": 320,  # unknown key, ignored by tiny-cuda-nn [ext]
+    "per_level_scale": 2,
+    "interpolation": "Linear",
+}
+
+_PRIMES = (1, 2654435761, 805459861, 3674653429)
+_U32 = 0xFFFFFFFF
+OUT_PAD = 16  # tiny-cuda-nn pads the output layer to 16 rows [ext]
+
+
+# ----------------------------------------------------------------------------------------------
+# hash-grid level table  (tiny-cuda-nn grid.h, GridEncodingTemplated ctor) [ext]
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class GridLevels:
+    n_dims: int
+    n_levels: int
+    n_features: int
+    scales: Tuple[float, ...]        # float32-valued
+    resolutions: Tuple[int, ...]
+    entries: Tuple[int, ...]         # "hashmap_size" of each level
+    offsets: Tuple[int, ...]         # prefix sums, len n_levels+1
+    hashed: Tuple[bool, ...]         # informational: does grid_index() take the hash branch?
+
+    @property
+    def n_table_params(self) -> int:
+        return self.offsets[-1] * self.n_features
+
+    @property
+    def n_encoded(self) -> int:
+        return self.n_levels * self.n_features
+
+
+def _u32(v: int) -> int:
+    return v & _U32
+
+
+def level_uses_hash(n_dims: int, entries: int, resolution: int) -> bool:
+    """Replays grid_index()'s stride loop for one level [ext]: hash iff the dense index range
+    (resolution**dims walked while stride <= entries) exceeds the level's entry count.
+
+    NOTE (unverifiable, tiny-cuda-nn source absent): upstream keeps ``stride`` in a uint32, so
+    for power-of-two resolutions >= 2**16 the product would wrap to 0 and skip the hash branch.
+    SURVEY.md section 8 a1/a2 (the build contract, incl. its touched-entry counts 3.04 M / 6.51 M)
+    specifies levels 6-15 (2-D) and 3-15 (3-D) as hashed, i.e. a non-wrapping stride; this
+    oracle and the kernels follow the contract.  See DESIGN.md "Q12".
+    """
+    stride = 1
+    dim = 0
+    while dim < n_dims and stride <= entries:
+        stride = stride * resolution
+        dim += 1
+    return entries < stride
+
+
+def make_grid_levels(n_dims: int, cfg: dict) -> GridLevels:
+    if cfg.get("otype", "Grid") not in ("Grid", "HashGrid") or cfg.get("type", "Hash") != "Hash":
+        raise ValueError("only otype=Grid/type=Hash encodings are on the IM-MoCo path")
+    if cfg.get("interpolation", "Linear") != "Linear":
+        raise ValueError("only Linear interpolation is on the IM-MoCo path")
+    n_levels = int(cfg.get("n_levels", 16))
+    n_feat = int(cfg.get("n_features_per_level", 2))
+    log2_t = int(cfg.get("log2_hashmap_size", 19))
+    base = int(cfg.get("base_resolution", 16))
+    pls = float(cfg.get("per_level_scale", 2.0))
+    log2_pls = math.log2(pls)
+    scales, ress, ents, offs, hashed = [], [], [], [0], []
+    for lvl in range(n_levels):
+        # grid_scale(): exp2f(level * log2_per_level_scale) * base_resolution - 1.0f
+        scale = float(torch.tensor(2.0 ** (lvl * log2_pls) * base - 1.0, dtype=torch.float32))
+        res = int(math.ceil(scale)) + 1
+        max_params = _U32 // 2
+        dense = res ** n_dims
+        n = max_params if float(dense) > float(max_params) else dense
+        n = (n + 7) // 8 * 8
+        n = min(n, 1 << log2_t)
+        scales.append(scale)
+        ress.append(res)
+        ents.append(n)
+        offs.append(offs[-1] + n)
+        hashed.append(level_uses_hash(n_dims, n, res))
+    return GridLevels(n_dims, n_levels, n_feat, tuple(scales), tuple(ress), tuple(ents),
+                      tuple(offs), tuple(hashed))
+
+
+def _mul_u32(q: torch.Tensor, c: int) -> torch.Tensor:
+    """(q * c) mod 2**32 for int64 tensors holding uint32 values, without int64 overflow."""
+    lo = c & 0xFFFF
+    hi = c >> 16
+    return (q * lo + (((q * hi) & 0xFFFF) << 16)) & _U32
+
+
+def grid_corner_index(q: Sequence[torch.Tensor], entries: int, res: int) -> torch.Tensor:
+    """grid_index<N_DIMS>() of tiny-cuda-nn [ext], uint32 arithmetic emulated in int64."""
+    n_dims = len(q)
+    stride = 1
+    idx = torch.zeros_like(q[0])
+    dim = 0
+    while dim < n_dims and stride <= entries:
+        idx = (idx + _mul_u32(q[dim], stride & _U32)) & _U32
+        stride = stride * res          # not wrapped, see level_uses_hash()
+        dim += 1
+    if entries < stride:
+        idx = torch.zeros_like(q[0])
+        for d in range(n_dims):
+            idx = idx ^ _mul_u32(q[d], _PRIMES[d])
+    return idx % entries
+
+
+def hashgrid_taps(x: torch.Tensor, lv: GridLevels, level: int):
+    """Corner indices (n_corners, N) int64 and weights (n_corners, N) fp32 of one level.
+
+    pos = fmaf(scale, x, 0.5); cell = floor(pos); frac = pos - cell   (grid.h pos_fract) [ext]
+    """
+    scale = lv.scales[level]
+    res = lv.resolutions[level]
+    ent = lv.entries[level]
+    pos = (x.double() * scale + 0.5).float()           # == fmaf in fp32 (exact product in fp64)
+    cell_f = torch.floor(pos)
+    frac = pos - cell_f
+    cell = cell_f.to(torch.int64) & _U32               # (uint32)(int) cast: two's complement wrap
+    idxs, ws = [], []
+    for corner in range(1 << lv.n_dims):
+        q, w = [], None
+        for d in range(lv.n_dims):
+            bit = (corner >> d) & 1
+            q.append((cell[:, d] + bit) & _U32)
+            wd = frac[:, d] if bit else (1.0 - frac[:, d])
+            w = wd if w is None else w * wd
+        idxs.append(grid_corner_index(q, ent, res))
+        ws.append(w)
+    return torch.stack(idxs), torch.stack(ws)
+
+
+def all_taps(x: torch.Tensor, lv: GridLevels):
+    """Global row indices (L, C, N) int64 into the whole table and weights (L, C, N) fp32."""
+    idxs, ws = [], []
+    for level in range(lv.n_levels):
+        idx, w = hashgrid_taps(x, lv, level)
+        idxs.append(idx + lv.offsets[level])
+        ws.append(w)
+    return torch.stack(idxs), torch.stack(ws)
+
+
+class _GatherTaps(torch.autograd.Function):
+    """feats[l, n, :] = sum_c w[l,c,n] * table[idx[l,c,n], :]; backward = one serial index_add_
+    (deterministic), the scatter-add that tiny-cuda-nn's kernel_grid_backward performs [ext]."""
+
+    @staticmethod
+    def forward(ctx, table, idx, w):
+        ctx.save_for_backward(idx, w)
+        ctx.rows = table.shape[0]
+        return (w.unsqueeze(-1) * table[idx]).sum(1)
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, w = ctx.saved_tensors
+        contrib = (w.unsqueeze(-1) * gout.unsqueeze(1)).reshape(-1, gout.shape[-1])
+        grad = torch.zeros(ctx.rows, gout.shape[-1], dtype=gout.dtype, device=gout.device)
+        grad.index_add_(0, idx.reshape(-1), contrib)
+        return grad, None, None
+
+
+_TAP_CACHE = {}
+
+
+def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, lv: GridLevels, cache: bool = True) -> torch.Tensor:
+    """(N, n_dims) fp32 coords + (total_entries, F) table -> (N, n_levels*F), level-major.
+
+    Taps depend on the coordinates only (constant during an IM-MoCo fit, immoco.py:72-80), so
+    they are cached per input tensor."""
+    key = (x.data_ptr(), tuple(x.shape), x.device, x._version, lv, float(x.double().sum()))
+    taps = _TAP_CACHE.get(key) if cache else None
+    if taps is None:
+        taps = all_taps(x, lv)
+        if cache:
+            if len(_TAP_CACHE) > 4:
+                _TAP_CACHE.clear()
+            _TAP_CACHE[key] = taps
+    idx, w = taps
+    feats = _GatherTaps.apply(table, idx, w)              # (L, N, F)
+    return feats.permute(1, 0, 2).reshape(x.shape[0], -1)
+
+
+def touched_entries(x: torch.Tensor, lv: GridLevels) -> int:
+    """Number of distinct table entries any tap of ``x`` touches (SURVEY 8(d) T_img / T_mot)."""
+    total = 0
+    for level in range(lv.n_levels):
+        idx, _ = hashgrid_taps(x, lv, level)
+        total += int(torch.unique(idx).numel())
+    return total
+
+
+_ACTS = {
+    "relu": torch.relu,
+    "tanh": torch.tanh,
+    "none": lambda t: t,
+}
+
+
+def mlp_param_count(n_in_padded: int, net_cfg: dict) -> int:
+    width = int(net_cfg["n_neurons"])
+    n_hidden = int(net_cfg.get("n_hidden_layers", 1))
+    return width * n_in_padded + (n_hidden - 1) * width * width + OUT_PAD * width
+
+
+class NetworkWithInputEncoding(nn.Module):
+    """torch fp32 stand-in for ``tinycudann.NetworkWithInputEncoding`` (immoco.py:60-65).
+
+    One flat fp32 Parameter ``params`` = [W1 (width x 32) | ... | W_out (16 x width) | table]
+    (network first, then encoding) [ext].  No biases, hidden activation from the config,
+    output activation None, output rows >= n_output_dims are padding [ext].
+    """
+
+    def __init__(self, n_input_dims: int, n_output_dims: int, encoding_config: dict,
+                 network_config: dict, seed: int = 1337):
+        super().__init__()
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = n_output_dims
+        self.levels = make_grid_levels(n_input_dims, encoding_config)
+        self.width = int(network_config["n_neurons"])
+        self.n_hidden = int(network_config.get("n_hidden_layers", 1))
+        self.act = _ACTS[str(network_config.get("activation", "ReLU")).lower()]
+        if str(network_config.get("output_activation", "None")).lower() != "none":
+            raise ValueError("output_activation must be None on the IM-MoCo path")
+        self.n_enc = self.levels.n_encoded
+        self.n_mlp = mlp_param_count(self.n_enc, network_config)
+        self.params = nn.Parameter(init_params(self.levels, network_config, seed))
+
+    def split(self, params: Optional[torch.Tensor] = None):
+        p = self.params if params is None else params
+        w, ofs = [], 0
+        n_in = self.n_enc
+        for _ in range(self.n_hidden):
+            w.append(p[ofs: ofs + self.width * n_in].view(self.width, n_in))
+            ofs += self.width * n_in
+            n_in = self.width
+        w.append(p[ofs: ofs + OUT_PAD * self.width].view(OUT_PAD, self.width))
+        ofs += OUT_PAD * self.width
+        table = p[ofs:].view(-1, self.levels.n_features)
+        return w, table
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        _, table = self.split()
+        return hashgrid_encode(x, table, self.levels)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        w, table = self.split()
+        h = hashgrid_encode(x.float(), table, self.levels)
+        for wi in w[:-1]:
+            h = self.act(h @ wi.t())
+        return (h @ w[-1].t())[:, : self.n_output_dims]
+
+
+def init_params(lv: GridLevels, network_config: dict, seed: int) -> torch.Tensor:
+    """Seeded initial parameters: MLP Xavier-uniform, table U(-1e-4, 1e-4) [ext semantics].
+
+    tiny-cuda-nn's own RNG stream cannot be reproduced; tests inject the SAME tensor on both
+    sides.  Generated on the CPU generator so the values are identical on every box.
+    """
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    width = int(network_config["n_neurons"])
+    n_hidden = int(network_config.get("n_hidden_layers", 1))
+    chunks = []
+    n_in = lv.n_encoded
+    for _ in range(n_hidden):
+        bound = math.sqrt(6.0 / (n_in + width))
+        chunks.append((torch.rand(width * n_in, generator=g) * 2 - 1) * bound)
+        n_in = width
+    bound = math.sqrt(6.0 / (n_in + OUT_PAD))
+    chunks.append((torch.rand(OUT_PAD * n_in, generator=g) * 2 - 1) * bound)
+    chunks.append((torch.rand(lv.n_table_params, generator=g) * 2 - 1) * 1e-4)
+    return torch.cat(chunks).float()
+
+
+class FourierNetworkWithInputEncoding(nn.Module):
+    """Config-1 timing baseline ONLY: Fourier features + same MLP widths.
+
+    gamma(x) = [sin(2 pi B x), cos(2 pi B x)],  B ~ N(0, sigma^2) in R^{16 x d}, seeded -> 32 features.
+    The reference contains no such encoder; this is not a parity target.
+    """
+
+    def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config,
+                 seed: int = 1337, sigma: float = 10.0):
+        super().__init__()
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed)
+        self.register_buffer("B", torch.randn(16, n_input_dims, generator=g) * sigma)
+        width = int(network_config["n_neurons"])
+        self.act = _ACTS[str(network_config.get("activation", "ReLU")).lower()]
+        self.n_output_dims = n_output_dims
+        b1 = math.sqrt(6.0 / (32 + width))
+        b2 = math.sqrt(6.0 / (width + OUT_PAD))
+        self.params = nn.Parameter(torch.cat([
+            (torch.rand(width * 32, generator=g) * 2 - 1) * b1,
+            (torch.rand(OUT_PAD * width, generator=g) * 2 - 1) * b2]).float())
+        self.width = width
+
+    def forward(self, x):
+        w1 = self.params[: self.width * 32].view(self.width, 32)
+        w2 = self.params[self.width * 32:].view(OUT_PAD, self.width)
+        ang = 2.0 * math.pi * (x.float() @ self.B.t())
+        e = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
+        return (self.act(e @ w1.t()) @ w2.t())[:, : self.n_output_dims]
+
+
+# ----------------------------------------------------------------------------------------------
+# MRI operators and losses
+# ----------------------------------------------------------------------------------------------
+def FFT(x: torch.Tensor) -> torch.Tensor:
+    """Centred un-normalised 2-D FFT over the last two dims (src/utils/data_utils.py:29-30)."""
+    d = (-2, -1)
+    return torch.fft.fftshift(torch.fft.fftn(torch.fft.ifftshift(x, dim=d), dim=d), dim=d)
+
+
+def IFFT(x: torch.Tensor) -> torch.Tensor:
+    """Centred 1/N-normalised inverse (src/utils/data_utils.py:33-34)."""
+    d = (-2, -1)
+    return torch.fft.ifftshift(torch.fft.ifftn(torch.fft.fftshift(x, dim=d), dim=d), dim=d)
+
+
+def gradient_entropy(img: torch.Tensor) -> torch.Tensor:
+    """-sum g*log(g+1e-24), g = |d/dx| + |d/dy| with zero padded last col/row (losses.py:20-40)."""
+    gx = (img[:, :-1] - img[:, 1:]).abs()
+    gy = (img[:-1, :] - img[1:, :]).abs()
+    g = F.pad(gx, (0, 1, 0, 0)) + F.pad(gy, (0, 0, 0, 1))
+    return -(g * torch.log(g + 1e-24)).sum()
+
+
+class GradientEntropyLoss(nn.Module):
+    def forward(self, x):
+        return gradient_entropy(x)
+
+
+def make_grids(sizes, device="cpu") -> torch.Tensor:
+    """(prod(sizes), len(sizes)) coords, each axis linspace(-1,1,s), "ij" order (immoco.py:48-53)."""
+    axes = [torch.linspace(-1, 1, s, device=device) for s in sizes]
+    return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, len(sizes))
+
+
+def identity_grid(h: int, w: int, device="cpu") -> torch.Tensor:
+    """(1,H,W,2) affine_grid of the identity, align_corners=True (immoco.py:72-76)."""
+    theta = torch.eye(2, 3, device=device).unsqueeze(0)
+    return F.affine_grid(theta, torch.Size((1, 1, h, w)), align_corners=True)
+
+
+class IMMoCo(nn.Module):
+    """Forward model of immoco.py:56-113 on top of the stand-in INRs."""
+
+    def __init__(self, masks: torch.Tensor, inr_cls=NetworkWithInputEncoding,
+                 image_params: Optional[torch.Tensor] = None,
+                 motion_params: Optional[torch.Tensor] = None, seed: int = 1337):
+        super().__init__()
+        self.image_inr = inr_cls(2, 2, ENCODING_CONFIG, IMAGE_NETWORK_CONFIG, seed=seed)
+        self.motion_inr = inr_cls(3, 2, ENCODING_CONFIG, MOTION_NETWORK_CONFIG, seed=seed + 1)
+        if image_params is not None:
+            self.image_inr.params.data.copy_(image_params)
+        if motion_params is not None:
+            self.motion_inr.params.data.copy_(motion_params)
+        self.masks = masks
+        self.num_movements, self.x, self.num_lines = masks.shape
+        self.device = masks.device
+        self.identy_grid = identity_grid(self.x, self.num_lines, device=self.device)
+        self.input_grid = make_grids((self.num_movements, self.x, self.num_lines), device=self.device)
+        self.to(self.device)
+
+    def image(self) -> torch.Tensor:
+        out = self.image_inr(self.identy_grid.view(-1, 2)).float().view(self.x, self.num_lines, 2)
+        return torch.complex(out[..., 0], out[..., 1])
+
+    def displacement(self) -> torch.Tensor:
+        """tanh(motion_inr(m,row,col)) -> (M,H,W,2); channel 0 moves x(col), 1 moves y(row)."""
+        if self.num_movements == 0:
+            return torch.zeros(0, self.x, self.num_lines, 2, device=self.device)
+        return self.motion_inr(self.input_grid).float().tanh().view(
+            self.num_movements, self.x, self.num_lines, 2)
+
+    def moved_images(self, image: torch.Tensor, disp_fn) -> torch.Tensor:
+        # op order follows immoco.py:91-107 (repeat, then motion INR, then grid_sample) so that
+        # autograd accumulates d(image) in the same order as the reference
+        m = self.num_movements
+        images = image.unsqueeze(0).repeat(m, 1, 1)
+        grids = disp_fn() + self.identy_grid.view(1, self.x, self.num_lines, 2)
+        src = torch.view_as_real(images).permute(0, 3, 1, 2)
+        out = F.grid_sample(src, grids, mode="bilinear", align_corners=False, padding_mode="zeros")
+        return torch.view_as_complex(out.permute(0, 2, 3, 1).contiguous())
+
+    def forward(self):
+        image = self.image()
+        if self.num_movements > 0:
+            moved = self.moved_images(image, self.displacement)
+            k = FFT(image) * (1 - self.masks.sum(0)).float() + (FFT(moved) * self.masks.float()).sum(0)
+        else:   # M == 0 is undefined in the reference: static branch only
+            k = FFT(image) * (1 - self.masks.sum(0)).float()
+        return k, image
+
+
+def lambda_schedule(iters: int, lambda_ge: float, variant: str = "main") -> List[float]:
+    """lambda used at each iteration j (immoco.py:180-181; variant test_immoco_downstream.py:189-190)."""
+    lams, lam = [], float(lambda_ge)
+    for j in range(iters):
+        lams.append(lam)
+        if variant == "main":
+            if j % (iters // 10) and j > (iters // 2):
+                lam *= 0.5
+        else:
+            if j % 10 == 0 and j > 80:
+                lam *= 0.5
+    return lams
+
+
+class LoopState:
+    """The state and one-iteration body of immoco.py:134-181 (model, normalised k-space, Adam),
+    exposed step-wise so that bench.py can time a bounded sample of iterations on the CPU."""
+
+    def __init__(self, kspace_corr, masks, iters, learning_rate=1e-2, lambda_ge=1e-2, *,
+                 inr_cls=NetworkWithInputEncoding, image_params=None, motion_params=None,
+                 kmax: float = 16000.0, variant: str = "main", seed: int = 1337):
+        self.model = IMMoCo(masks, inr_cls=inr_cls, image_params=image_params,
+                            motion_params=motion_params, seed=seed)
+        scale = kspace_corr.abs().max()
+        self.k_in = kspace_corr.div(scale).mul(kmax).clone().detach().to(masks.device)
+        self.opt = torch.optim.Adam([
+            {"params": self.model.motion_inr.parameters(), "lr": learning_rate},
+            {"params": self.model.image_inr.parameters(), "lr": learning_rate},
+        ])
+        self.lams = lambda_schedule(iters, lambda_ge, variant)   # ZeroDivisionError for iters<10 (Q3)
+        self.image = self.k_fwd = None
+
+    def step(self, j: int) -> torch.Tensor:
+        self.opt.zero_grad()
+        self.k_fwd, self.image = self.model()
+        loss = F.mse_loss(torch.view_as_real(self.k_fwd), torch.view_as_real(self.k_in)) \
+            + gradient_entropy(self.image).mul(self.lams[j])
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+
+def imcoco_motion_correction(kspace_corr, masks, iters=200, learning_rate=1e-2, lambda_ge=1e-2,
+                             debug=False, *, inr_cls=NetworkWithInputEncoding, image_params=None,
+                             motion_params=None, kmax: float = 16000.0, variant: str = "main",
+                             return_trace: bool = False, seed: int = 1337):
+    """Optimisation loop of immoco.py:116-206 (restated; no plotting).
+
+    Returns (image_prior, kspace_forward) of the LAST forward (before the last Adam step), plus
+    the per-step loss list when ``return_trace``.
+    """
+    st = LoopState(kspace_corr, masks, iters, learning_rate, lambda_ge, inr_cls=inr_cls,
+                   image_params=image_params, motion_params=motion_params, kmax=kmax,
+                   variant=variant, seed=seed)
+    trace = []
+    for j in range(iters):
+        loss = st.step(j)
+        if return_trace or debug:
+            trace.append(float(loss))
+    if return_trace:
+        return st.image, st.k_fwd, trace
+    return st.image, st.k_fwd
+
+
+# ----------------------------------------------------------------------------------------------
+# kld-net -> movement groups  (src/utils/motion_utils.py:56-109, test_immoco.py:59-61)
+# ----------------------------------------------------------------------------------------------
+def extract_movement_groups(motionline_indcies: torch.Tensor, make_list: bool = False,
+                            height: Optional[int] = None) -> torch.Tensor:
+    """Run-length labelling of detected phase-encode lines.
+
+    A label is given to every detected line; the label increments after a line whose right
+    neighbour is not detected.  ``height`` generalises the reference's square (W,W) output to
+    (H,W); None keeps the reference's square shape.
+    """
+    lines = motionline_indcies
+    w = lines.shape[0]
+    h = w if height is None else height
+    flags = [bool(v) for v in (lines == 1).tolist()]
+    labels = [0] * w
+    count = 1
+    for i in range(w):
+        if not flags[i]:
+            continue
+        labels[i] = count
+        if i != w - 1 and not flags[i + 1]:
+            count += 1
+    groups = torch.tensor(labels, dtype=torch.long, device=lines.device).unsqueeze(0).repeat(h, 1)
+    if not make_list:
+        return groups
+    n = int(torch.unique(groups).nonzero().numel())
+    out = torch.zeros((n, h, w), dtype=torch.long, device=lines.device)
+    for i in range(n):
+        out[i, groups == i + 1] = 1
+    return out
+
+
+def lines_from_mask(mask: torch.Tensor) -> torch.Tensor:
+    """Column vote of test_immoco.py:59-61: mask.sum(0)/H > 0.2 -> bool (W,)."""
+    return mask.sum(0).div(mask.shape[0]) > 0.2
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic data  (src/utils/motion_utils.py:7-34,112-202 semantics; SURVEY 8(d) phantom)
+# ----------------------------------------------------------------------------------------------
+def make_phantom(h: int, w: int, seed: int) -> torch.Tensor:
+    """Complex64 phantom: 12 soft-edged ellipses times a smooth phase, |.| <= 1."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+    mag = torch.zeros(h, w)
+    for _ in range(12):
+        cx, cy = (torch.rand(2, generator=g) - 0.5).tolist()
+        ax, ay = (torch.rand(2, generator=g) * 0.40 + 0.05).tolist()
+        amp = float(torch.rand(1, generator=g) * 0.9 + 0.1)
+        ang = float(torch.rand(1, generator=g) * math.pi)
+        xr = (xx - cx) * math.cos(ang) + (yy - cy) * math.sin(ang)
+        yr = -(xx - cx) * math.sin(ang) + (yy - cy) * math.cos(ang)
+        r = torch.sqrt((xr / ax) ** 2 + (yr / ay) ** 2)
+        mag = mag + amp * torch.sigmoid((1.0 - r) * 12.0)
+    mag = mag / mag.max()
+    phi = float(torch.rand(1, generator=g) * 2 * math.pi)
+    phase = 0.3 * torch.sin(2.0 * xx + phi)
+    return torch.polar(mag, phase).to(torch.complex64)
+
+
+def _gap_positions(size: int, n: int, mingap: int) -> torch.Tensor:
+    # generate_list (motion_utils.py:7-24): random starts with a minimum gap
+    slack = size - mingap * (n - 1)
+    steps = int(torch.randint(0, slack, (1,))[0])
+    inc = torch.hstack([torch.ones((steps,), dtype=torch.long), torch.zeros((n,), dtype=torch.long)])
+    inc = inc[torch.randperm(inc.shape[0])]
+    locs = torch.argwhere(inc == 0).flatten()
+    return torch.cumsum(inc, dim=0)[locs] + mingap * torch.arange(0, n)
+
+
+def _rand_nonzero(lo: int, hi: int) -> torch.Tensor:
+    # get_rand_int (motion_utils.py:27-34): 0 is replaced by 1
+    r = torch.randint(lo, hi, size=(1,))
+    return r + 1 if int(r) == 0 else r
+
+
+def motion_simulation2D(image_2d: torch.Tensor, n_movements: Optional[int] = None):
+    """Rigid per-movement corruption of k-space line windows (motion_utils.py:121-202).
+
+    Consumes the GLOBAL torch RNG in the same order as the reference so that a common
+    ``torch.manual_seed`` gives identical outputs.
+    """
+    k = FFT(image_2d)
+    h, w = k.shape
+    if n_movements is None:
+        n_movements = int(_rand_nonzero(5, 20))
+    starts = _gap_positions(w, n_movements, w // n_movements)
+    mask = torch.zeros((h, w), dtype=torch.long)
+    rot = torch.zeros((n_movements,))
+    trans = torch.zeros((n_movements, 2))
+    for m in range(n_movements):
+        sx = int(_rand_nonzero(-10, 10))
+        sy = int(_rand_nonzero(-10, 10))
+        ang = _rand_nonzero(-10, 10)
+        a = torch.deg2rad(ang)
+        theta = torch.tensor([[1, 0, sx], [0, 1, sy]]).float()
+        theta[:2, :2] = torch.tensor([[torch.cos(a), -torch.sin(a)], [torch.sin(a), torch.cos(a)]])
+        theta = theta.view(1, 2, 3)
+        theta[:, :, -1] /= (torch.tensor(image_2d[0, ...].shape) * 2.0) - 1
+        grid = F.affine_grid(theta, (1, 1, h, w), align_corners=True).to(image_2d.device).float()
+        parts = [F.grid_sample(c[None, None], grid, mode="bilinear", padding_mode="border",
+                               align_corners=False) for c in (image_2d.real, image_2d.imag)]
+        moved = parts[0] + 1j * parts[1]
+        k_m = FFT(moved).squeeze()
+        w0 = starts[m]
+        w1 = w0 + _rand_nonzero(1, 10)
+        k[..., w0:w1] = k_m[..., w0:w1]
+        mask[:, w0:w1] = 1
+        rot[m] = ang
+        trans[m, :] = torch.tensor([sx, sy])
+    return k, mask, rot, trans
+
+
+def make_case(h: int, w: int, n_movements: int, seed: int):
+    """One synthetic slice: phantom, corrupted k-space, (M,H,W) group masks."""
+    img = make_phantom(h, w, seed)
+    torch.manual_seed(seed)
+    k_motion, mask, rot, trans = motion_simulation2D(img, n_movements)
+    masks = extract_movement_groups(lines_from_mask(mask), make_list=True, height=h)
+    return {"image": img, "kspace_motion": k_motion.to(torch.complex64), "mask": mask,
+            "masks": masks, "rotation": rot, "translation": trans}
+
+
+# ----------------------------------------------------------------------------------------------
+# metrics  (src/utils/evaluate.py:19-47,57-80; piq.ssim restated [ext])
+# ----------------------------------------------------------------------------------------------
+def normalize01(x: torch.Tensor) -> torch.Tensor:
+    return (x - x.min()) / (x.max() - x.min() + 1e-24)
+
+
+def psnr01(pred: torch.Tensor, gt: torch.Tensor) -> float:
+    mse = torch.mean((pred - gt) ** 2)
+    return float(20 * torch.log10(1.0 / torch.sqrt(mse)))
+
+
+def ssim01(pred: torch.Tensor, gt: torch.Tensor, kernel_size: int = 11, sigma: float = 1.5) -> float:
+    """piq.ssim(kernel_size=11, data_range=1) on (H,W) images in [0,1] [ext]."""
+    x = pred[None, None].double()
+    y = gt[None, None].double()
+    f = max(1, round(min(x.shape[-2:]) / 256))
+    if f > 1:
+        x, y = F.avg_pool2d(x, f), F.avg_pool2d(y, f)
+    c = torch.arange(kernel_size, dtype=torch.float64) - (kernel_size - 1) / 2.0
+    g = torch.exp(-(c ** 2) / (2 * sigma ** 2))
+    k2 = torch.outer(g, g)
+    k2 = (k2 / k2.sum())[None, None]
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    mx, my = F.conv2d(x, k2), F.conv2d(y, k2)
+    sxx = F.conv2d(x * x, k2) - mx * mx
+    syy = F.conv2d(y * y, k2) - my * my
+    sxy = F.conv2d(x * y, k2) - mx * my
+    cs = (2 * sxy + c2) / (sxx + syy + c2)
+    ss = (2 * mx * my + c1) / (mx * mx + my * my + c1) * cs
+    return float(ss.mean())
+
+
+def crop_metrics(pred_abs: torch.Tensor, gt_abs: torch.Tensor):
+    """Central-half crop + min-max normalise + PSNR/SSIM/RMSE (test_immoco.py:74-85)."""
+    h, w = gt_abs.shape
+    ch, cw = int(h / 4), int(w / 4)
+    p = normalize01(pred_abs[ch:-ch, cw:-cw].float())
+    g = normalize01(gt_abs[ch:-ch, cw:-cw].float())
+    return {"psnr": psnr01(p, g), "ssim": ssim01(p, g),
+            "rmse": float(torch.sqrt(torch.mean((p - g) ** 2)))}

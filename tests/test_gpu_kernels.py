@@ -1,0 +1,198 @@
+"""GPU: every CUDA entry point against the oracle (torch fp32) on the same seeded inputs.
+All calls go through the C ABI (ctypes) via the reference-facing Python wrappers."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import miccai24_immoco_b200 as mb
+from miccai24_immoco_b200 import _native as nat
+from miccai24_immoco_b200.encoding import grid_spec, mlp_spec
+from miccai24_immoco_b200.ops import twiddle_table
+from oracle import immoco_oracle as orc
+from tests.gpu_util import case_params, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mb.build()
+    yield
+
+
+def _coords(dims, kind):
+    if kind == "grid":
+        return (orc.identity_grid(320, 320).view(-1, 2) if dims == 2 else orc.make_grids((4, 320, 320))).contiguous()
+    g = torch.Generator().manual_seed(dims * 7 + len(kind))
+    n = {"ragged": 1001, "tiny": 1}[kind]
+    return (torch.rand(n, dims, generator=g) * 3.0 - 1.5).contiguous()       # incl. negative cells
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("kind", ["grid", "ragged", "tiny"])
+def test_hashgrid_forward_and_backward(native_lib, dims, kind):
+    gs = grid_spec(dims, mb.encoding_config)
+    lv = orc.make_grid_levels(dims, orc.ENCODING_CONFIG)
+    x = _coords(dims, kind).to(DEV)
+    n = x.shape[0]
+    g = torch.Generator().manual_seed(3)
+    table = ((torch.rand(gs.n_rows, 2, generator=g) * 2 - 1) * 1e-1).to(DEV).requires_grad_(True)
+    enc = torch.empty((16, n, 2), device=DEV)
+    d = gs.desc()
+    nat.check(native_lib.immoco_hashgrid_fwd(C.byref(d), x.data_ptr(), table.data_ptr(), enc.data_ptr(), n, _s()), "fwd")
+    ref = orc.hashgrid_encode(x, table, lv, cache=False)                      # (N, 32)
+    got = enc.permute(1, 0, 2).reshape(n, 32)
+    assert rel_l2(got, ref) < 1e-6
+    assert float((got - ref).abs().max()) < 1e-6
+    # backward: scatter-add of a random cotangent
+    d_enc = torch.randn(16, n, 2, generator=torch.Generator().manual_seed(4)).to(DEV)
+    grad = torch.zeros_like(table)
+    nat.check(native_lib.immoco_hashgrid_bwd(C.byref(d), x.data_ptr(), d_enc.data_ptr(), grad.data_ptr(), n, _s()), "bwd")
+    (ref * d_enc.permute(1, 0, 2).reshape(n, 32)).sum().backward()
+    assert rel_l2(grad, table.grad) < 2e-6
+    untouched = table.grad.abs().sum(1) == 0
+    assert bool((grad[untouched] == 0).all())
+
+
+@pytest.mark.parametrize("width,act", [(256, "relu"), (64, "tanh"), (64, "relu"), (256, "tanh")])
+@pytest.mark.parametrize("n", [1, 127, 128, 1000, 40000])
+def test_mlp_forward_and_backward(native_lib, width, act, n):
+    g = torch.Generator().manual_seed(width + n)
+    enc = (torch.randn(16, n, 2, generator=g) * 0.5).to(DEV)
+    w1 = (torch.randn(width, 32, generator=g) * 0.2).to(DEV).requires_grad_(True)
+    w2 = (torch.randn(16, width, generator=g) * 0.2).to(DEV).requires_grad_(True)
+    e = enc.permute(1, 0, 2).reshape(n, 32).clone().requires_grad_(True)
+    f = torch.relu if act == "relu" else torch.tanh
+    code = nat.ACT_RELU if act == "relu" else nat.ACT_TANH
+    for out_tanh in (0, 1):
+        out = torch.empty((n, 2), device=DEV)
+        nat.check(native_lib.immoco_mlp_fwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), n,
+                                            width, code, out_tanh, _s()), "mlp_fwd")
+        ref = (f(e @ w1.t()) @ w2.t())[:, :2]
+        if out_tanh:
+            ref = ref.tanh()
+        assert rel_l2(out, ref) < 2e-6
+    ref = (f(e @ w1.t()) @ w2.t())[:, :2]
+    d_out = torch.randn(n, 2, generator=g).to(DEV)
+    (ref * d_out).sum().backward()
+    d_enc = torch.empty_like(enc)
+    g1 = torch.zeros_like(w1)
+    g2 = torch.zeros_like(w2)
+    nat.check(native_lib.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(),
+                                        d_enc.data_ptr(), g1.data_ptr(), g2.data_ptr(), n, width, code, _s()), "mlp_bwd")
+    assert rel_l2(d_enc.permute(1, 0, 2).reshape(n, 32), e.grad) < 5e-6
+    assert rel_l2(g1, w1.grad) < 5e-6
+    assert rel_l2(g2[:2], w2.grad[:2]) < 5e-6
+    assert bool((g2[2:] == 0).all())                                          # padded rows get no gradient
+
+
+@pytest.mark.parametrize("dims,cfg", [(2, "image"), (3, "motion")])
+def test_network_with_input_encoding_module(dims, cfg):
+    net_cfg = mb.network_config if cfg == "image" else mb.mot_network_config
+    o = orc.NetworkWithInputEncoding(dims, 2, orc.ENCODING_CONFIG, net_cfg, seed=11).to(DEV)
+    m = mb.NetworkWithInputEncoding(dims, 2, mb.encoding_config, net_cfg, seed=99)
+    assert m.params.shape == o.params.shape and m.params.is_cuda
+    with torch.no_grad():
+        m.params.copy_(o.params)
+    x = (orc.identity_grid(96, 80).view(-1, 2) if dims == 2 else orc.make_grids((2, 48, 40))).to(DEV)
+    ya, yb = m(x), o(x)
+    assert ya.shape == yb.shape and ya.dtype == torch.float32
+    assert rel_l2(ya, yb) < 1e-5
+    d = torch.randn(ya.shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    (ya * d).sum().backward()
+    (yb * d).sum().backward()
+    n_mlp = m.mlp.n_params
+    assert rel_l2(m.params.grad[:n_mlp], o.params.grad[:n_mlp]) < 1e-4
+    assert rel_l2(m.params.grad[n_mlp:], o.params.grad[n_mlp:]) < 1e-4
+    with pytest.raises(RuntimeError):
+        m(x.cpu())
+
+
+@pytest.mark.parametrize("shape", [(320, 320), (640, 368), (64, 46), (3, 32, 20), (2, 2, 16, 24)])
+def test_fft_ifft_and_adjoints(shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.complex(torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)).to(DEV)
+    ref = orc.FFT(x)
+    assert rel_l2(mb.FFT(x), ref) < 2e-6
+    assert rel_l2(mb.IFFT(x), orc.IFFT(x)) < 2e-6
+    assert rel_l2(mb.IFFT(mb.FFT(x)), x) < 2e-6
+    # adjoint through autograd
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    c = torch.complex(torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)).to(DEV)
+    (mb.FFT(xa) * c).real.sum().backward()
+    (orc.FFT(xb) * c).real.sum().backward()
+    assert rel_l2(xa.grad, xb.grad) < 2e-6
+    xa.grad = None
+    xb.grad = None
+    (mb.IFFT(xa) * c).real.sum().backward()
+    (orc.IFFT(xb) * c).real.sum().backward()
+    assert rel_l2(xa.grad, xb.grad) < 2e-6
+
+
+def test_fft_golden_from_reference(golden_dir):
+    ops = np.load(os.path.join(golden_dir, "ops_small.npz"))
+    for hw in ("32x32", "48x20", "64x46"):
+        x = torch.from_numpy(ops[f"fft_in_{hw}"]).to(DEV)
+        assert rel_l2(mb.FFT(x), torch.from_numpy(ops[f"fft_out_{hw}"])) < 2e-6
+    with pytest.raises(NotImplementedError):
+        mb.FFT(torch.zeros(7, 9, dtype=torch.complex64, device=DEV))          # odd sizes: not on the path
+
+
+def test_gradient_entropy_value_and_grad(golden_dir):
+    ops = np.load(os.path.join(golden_dir, "ops_small.npz"))
+    x = torch.from_numpy(ops["ge_in"]).to(DEV).requires_grad_(True)
+    val = mb.GradientEntropyLoss()(x)
+    val.backward()
+    assert abs(float(val) - float(ops["ge_val"])) <= 2e-6 * abs(float(ops["ge_val"]))
+    assert rel_l2(x.grad, torch.from_numpy(ops["ge_grad"])) < 5e-6
+    g = torch.Generator().manual_seed(5)
+    y = torch.complex(torch.randn(320, 320, generator=g), torch.randn(320, 320, generator=g)).to(DEV)
+    y[10, 10] = y[10, 11]
+    ya = y.clone().requires_grad_(True)
+    yb = y.clone().requires_grad_(True)
+    a = mb.GradientEntropyLoss()(ya)
+    b = orc.gradient_entropy(yb)
+    (a * 0.37).backward()
+    (b * 0.37).backward()
+    assert abs(float(a) - float(b)) <= 2e-6 * abs(float(b))
+    assert rel_l2(ya.grad, yb.grad) < 5e-6
+
+
+def test_adam_step_matches_torch(native_lib):
+    n = 1_000_002                                                            # exercises the scalar tail
+    g = torch.Generator().manual_seed(9)
+    p = torch.randn(n, generator=g).to(DEV)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 5):
+        grad = (torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-6, 3, (1,), generator=g)))).to(DEV)
+        grad[::7] = 0.0
+        gbuf = grad.clone()
+        nat.check(native_lib.immoco_adam_step(p.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), n,
+                                              1e-2, 0.9, 0.999, 1e-8, step, 1, _s()), "adam")
+        ref.grad = grad.clone()
+        opt.step()
+        assert bool((gbuf == 0).all())                                       # zero_grad fused
+        assert float((p - ref.detach()).abs().max()) < 2e-6
+    st = opt.state[ref]
+    assert rel_l2(m, st["exp_avg"]) < 1e-6 and rel_l2(v, st["exp_avg_sq"]) < 1e-6
+    # untouched (zero-gradient) entries never move: m = v = 0
+    z, zm, zv = (torch.zeros(1024, device=DEV) for _ in range(3))
+    p0 = torch.randn(1024, device=DEV)
+    p1 = p0.clone()
+    nat.check(native_lib.immoco_adam_step(p1.data_ptr(), z.data_ptr(), zm.data_ptr(), zv.data_ptr(),
+                                          1024, 1e-2, 0.9, 0.999, 1e-8, 1, 1, _s()), "adam")
+    assert torch.equal(p0, p1)
