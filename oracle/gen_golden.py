@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--full", action="store_true", help="also the 320x320, n_M=4 case (slow)")
     ap.add_argument("--full-iters", type=int, default=200)
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--full-seed", type=int, default=1004,
+                    help="slice seed of the 320x320 case (1004: corrupted PSNR 29.6 dB / SSIM 0.953)")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     out_dir = os.path.join(ROOT, "tests", "golden")
@@ -242,7 +244,7 @@ def main():
         loop_golden(ref_immoco, "s32_m1", 32, 1, seed=6, iters=20, out_dir=out_dir)
     if args.full:
         print(f"[loop 320x320, n_M=4, {args.full_iters} its]")
-        loop_golden(ref_immoco, f"c2_i{args.full_iters}", 320, 4, seed=1000, iters=args.full_iters,
+        loop_golden(ref_immoco, f"c2_i{args.full_iters}", 320, 4, seed=args.full_seed, iters=args.full_iters,
                     out_dir=out_dir, check_restatement=False, small_payload=True)
     print("done")
 
