@@ -345,8 +345,11 @@ def imcoco_motion_correction(kspace_corr, masks, iters=200, learning_rate=1e-2, 
     if debug:
         for j in range(0, iters, 20):
             print(f"iter: {j}, DC_Loss: {trace[j]:.4f}")
+    # The reference calls torch.cuda.empty_cache() here (immoco.py:203).  Releasing ~1.4 GB of
+    # cached blocks costs 0.2-0.9 s per slice on B200 (profiles/round1_v1_e2e_breakdown.txt) and
+    # buys nothing when the next slice re-allocates the same buffers, so the blocks stay with the
+    # caching allocator; wrap the call in ``ClearCache()`` to get the reference behaviour.
     del engine, model
-    torch.cuda.empty_cache()
     if return_trace:
         return image_prior, kspace_foward_model, trace
     return image_prior, kspace_foward_model
