@@ -63,6 +63,14 @@ int immoco_hashgrid_fwd(const immoco_grid_desc* grid, const float* coords, const
 int immoco_hashgrid_bwd(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
                         float* grad_table, int64_t n_points, void* stream);
 
+/* level-range variants of the two calls above: only levels [level_begin, level_end) */
+int immoco_hashgrid_fwd_levels(const immoco_grid_desc* grid, const float* coords, const float* table,
+                               float* enc, int64_t n_points, int32_t level_begin, int32_t level_end,
+                               void* stream);
+int immoco_hashgrid_bwd_levels(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
+                               float* grad_table, int64_t n_points, int32_t level_begin,
+                               int32_t level_end, void* stream);
+
 /* ---- (2) INR MLP: replaces the network half of tcnn.NetworkWithInputEncoding
  *          (configs at src/models/immoco.py:11-25).  One hidden layer of `width` (64 or 256),
  *          no biases, W1: width x 32, W2: 16 x width (rows >= 2 are padding).
@@ -73,6 +81,10 @@ int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2, float* ou
 int immoco_mlp_bwd(const float* enc, const float* w1, const float* w2, const float* d_out,
                    float* d_enc, float* g_w1, float* g_w2, int64_t n_points, int32_t width,
                    int32_t act, void* stream);
+/* MLP kernel selection for A/B checks: 0 = fp32 SIMT kernels, 1 = tcgen05 (kind::tf32, 3xTF32
+ * split, accumulators in TMEM).  Both satisfy the same fp32-parity tolerances. */
+int immoco_set_mlp_impl(int32_t impl);
+int immoco_get_mlp_impl(void);
 /* element-wise helper for the autograd wrapper: d_pre = d_post * (1 - y^2) */
 int immoco_tanh_bwd(const float* y, const float* d_post, float* d_pre, int64_t n, void* stream);
 
@@ -151,6 +163,9 @@ int immoco_profile_read(immoco_profile* prof, float* ms_sum);
 int immoco_fit_run(const immoco_fit* fit, int32_t it_begin, int32_t it_end,
                    const float* lambdas_host, void* stream, immoco_profile* prof,
                    int32_t profile_every);
+/* 1 (default): the image-INR branch of every non-instrumented iteration runs on an internal
+ * auxiliary stream, forked from / joined to `stream` with events; 0: everything on `stream`. */
+int immoco_set_branch_overlap(int32_t on);
 
 /* library/ABI version and the number of kernel launches one fit iteration issues */
 int immoco_abi_version(void);

@@ -16,6 +16,7 @@ from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_conf
                      network_config)
 from .motion_utils import extract_movement_groups, lines_from_mask  # noqa: F401
 from .ops import FFT, IFFT, GradientEntropyLoss, NetworkWithInputEncoding  # noqa: F401
+from .sharding import gather_images, reconstruct_slices, shard_indices  # noqa: F401
 
 __all__ = [
     "imcoco_motion_correction", "IMMoCo", "make_grids", "network_config", "mot_network_config",

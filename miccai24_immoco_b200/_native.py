@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libimmoco_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["hashgrid.cu", "mlp.cu", "forward_model.cu", "fit.cu"]
+SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu"]
 
 MAX_LEVELS = 16
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -73,9 +73,13 @@ _P = C.c_void_p
 _SIGNATURES = {
     "immoco_hashgrid_fwd": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, _P]),
     "immoco_hashgrid_bwd": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, _P]),
+    "immoco_hashgrid_fwd_levels": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "immoco_hashgrid_bwd_levels": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "immoco_mlp_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "immoco_tanh_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "immoco_set_mlp_impl": (C.c_int, [C.c_int32]),
+    "immoco_get_mlp_impl": (C.c_int, []),
     "immoco_fft2c": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32,
                                C.c_float, _P]),
     "immoco_forward_model": (C.c_int, [_P, _P, _P, C.POINTER(Lines), _P, _P, _P, _P, C.c_int32,
@@ -91,6 +95,7 @@ _SIGNATURES = {
     "immoco_profile_create": (_P, [C.c_int32]),
     "immoco_profile_destroy": (None, [_P]),
     "immoco_profile_read": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "immoco_set_branch_overlap": (C.c_int, [C.c_int32]),
     "immoco_abi_version": (C.c_int, []),
     "immoco_launches_per_iteration": (C.c_int, [C.c_int32]),
     "immoco_struct_sizes": (None, [C.POINTER(C.c_int32)]),

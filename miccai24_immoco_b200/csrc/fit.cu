@@ -153,6 +153,33 @@ extern "C" int immoco_profile_read(immoco_profile* p, float* ms_sum) {
   return n;
 }
 
+// ---- image-INR branch on a second stream --------------------------------------------------------
+// The two INR branches of an iteration are independent and stress different units
+// (hash-grid gathers / reductions: L2; MLPs: tensor pipe + SIMT epilogue), so the image branch runs on
+// an auxiliary non-blocking stream, forked and joined with events.  One aux stream + 4 events per
+// device are created on first use and live for the process (the library's only hidden state).
+struct AuxStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork_fwd = nullptr, join_fwd = nullptr, fork_bwd = nullptr, join_bwd = nullptr;
+  bool ok = false;
+};
+static AuxStream* aux_for_current_device() {
+  static AuxStream table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  AuxStream& a = table[dev];
+  if (!a.ok) {
+    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEvent_t* ev[4] = {&a.fork_fwd, &a.join_fwd, &a.fork_bwd, &a.join_bwd};
+    for (auto e : ev)
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a.ok = true;
+  }
+  return &a;
+}
+static int g_overlap = 1;
+extern "C" int immoco_set_branch_overlap(int32_t on) { g_overlap = on ? 1 : 0; return 0; }
+
 #define IMMOCO_MARK()                                                  \
   do {                                                                 \
     if (ev) { cudaEventRecord(ev[slot], (cudaStream_t)stream); }       \
@@ -181,12 +208,18 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     if (prof && profile_every > 0 && (it % profile_every) == profile_every - 1 && prof->used < prof->capacity)
       ev = prof->ev + (size_t)(prof->used++) * (prof->n_slots + 1);
     int slot = 0;
+    // instrumented iterations run serially on the caller's stream so per-kernel event times mean something
+    AuxStream* aux = (g_overlap && !ev && M > 0) ? aux_for_current_device() : nullptr;
+    cudaStream_t ms = (cudaStream_t)stream;
+    void* is = aux ? (void*)aux->stream : stream;       // stream of the image-INR branch
     IMMOCO_MARK();
     // ---- forward -------------------------------------------------------------------------------
-    IMMOCO_TRY(immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, stream));
+    if (aux) { cudaEventRecord(aux->fork_fwd, ms); cudaStreamWaitEvent(aux->stream, aux->fork_fwd, 0); }
+    IMMOCO_TRY(immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is));
     IMMOCO_MARK();  // slot 0: hashgrid_fwd_image
-    IMMOCO_TRY(immoco_mlp_fwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->image, P, wi, f->act_image, 0, stream));
+    IMMOCO_TRY(immoco_mlp_fwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->image, P, wi, f->act_image, 0, is));
     IMMOCO_MARK();  // 1: mlp_fwd_image
+    if (aux) cudaEventRecord(aux->join_fwd, aux->stream);
     if (M > 0) {
       IMMOCO_TRY(immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream));
     }
@@ -195,6 +228,7 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
       IMMOCO_TRY(immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream));
     }
     IMMOCO_MARK();  // 3: mlp_fwd_motion
+    if (aux) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
     IMMOCO_TRY(immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
     IMMOCO_MARK();  // 4: fft_rows
     IMMOCO_TRY(immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
@@ -211,6 +245,7 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
                                         f->d_image, f->d_disp, H, W, stream));
     }
     IMMOCO_MARK();  // 9: motion_rows_bwd
+    if (aux) { cudaEventRecord(aux->fork_bwd, ms); cudaStreamWaitEvent(aux->stream, aux->fork_bwd, 0); }
     if (M > 0) {
       IMMOCO_TRY(immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
                                 gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream));
@@ -221,10 +256,11 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     }
     IMMOCO_MARK();  // 11: hashgrid_bwd_motion
     IMMOCO_TRY(immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
-                              gi + (int64_t)wi * 32, P, wi, f->act_image, stream));
+                              gi + (int64_t)wi * 32, P, wi, f->act_image, is));
     IMMOCO_MARK();  // 12: mlp_bwd_image
-    IMMOCO_TRY(immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, stream));
+    IMMOCO_TRY(immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is));
     IMMOCO_MARK();  // 13: hashgrid_bwd_image
+    if (aux) { cudaEventRecord(aux->join_bwd, aux->stream); cudaStreamWaitEvent(ms, aux->join_bwd, 0); }
     // ---- update (zero_grad fused) ----------------------------------------------------------------
     IMMOCO_TRY(immoco_adam_step(f->params, f->grads, f->exp_avg, f->exp_avg_sq, f->n_motion + f->n_image,
                                 f->lr, f->beta1, f->beta2, f->eps, it + 1, 1, stream));

@@ -352,11 +352,24 @@ int launch_bwd(const float* enc, const float* w1, const float* w2, const float* 
 
 }  // namespace
 
+// implemented in mlp_tc.cu (tcgen05 / TMEM)
+int immoco_mlp_fwd_tc(const float* enc, const float* w1, const float* w2, float* out, int64_t n_points,
+                      int32_t width, int32_t act, int32_t out_tanh, void* stream);
+
+static int g_mlp_impl = 1;   // 1: tcgen05 3xTF32 (product path), 0: fp32 SIMT (A/B check kernels)
+extern "C" int immoco_set_mlp_impl(int32_t impl) {
+  if (impl != 0 && impl != 1) return IMMOCO_ERR_BAD_ARG;
+  g_mlp_impl = impl;
+  return 0;
+}
+extern "C" int immoco_get_mlp_impl(void) { return g_mlp_impl; }
+
 extern "C" int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2, float* out,
                               int64_t n_points, int32_t width, int32_t act, int32_t out_tanh,
                               void* stream) {
   if (n_points < 0 || n_points > 0x3fffffff) return IMMOCO_ERR_BAD_ARG;
   if (n_points == 0) return 0;
+  if (g_mlp_impl == 1) return immoco_mlp_fwd_tc(enc, w1, w2, out, n_points, width, act, out_tanh, stream);
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)n_points;
   if (width == 256 && act == IMMOCO_ACT_RELU) return launch_fwd<256, IMMOCO_ACT_RELU>(enc, w1, w2, out, n, out_tanh, s);
@@ -366,11 +379,15 @@ extern "C" int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2
   return IMMOCO_ERR_UNSUPPORTED;
 }
 
+int immoco_mlp_bwd_tc(const float* enc, const float* w1, const float* w2, const float* d_out, float* d_enc,
+                      float* g_w1, float* g_w2, int64_t n_points, int32_t width, int32_t act, void* stream);
+
 extern "C" int immoco_mlp_bwd(const float* enc, const float* w1, const float* w2, const float* d_out,
                               float* d_enc, float* g_w1, float* g_w2, int64_t n_points,
                               int32_t width, int32_t act, void* stream) {
   if (n_points < 0 || n_points > 0x3fffffff) return IMMOCO_ERR_BAD_ARG;
   if (n_points == 0) return 0;
+  if (g_mlp_impl == 1) return immoco_mlp_bwd_tc(enc, w1, w2, d_out, d_enc, g_w1, g_w2, n_points, width, act, stream);
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)n_points;
   if (width == 256 && act == IMMOCO_ACT_RELU) return launch_bwd<256, IMMOCO_ACT_RELU>(enc, w1, w2, d_out, d_enc, g_w1, g_w2, n, s);

@@ -144,6 +144,18 @@ def _fft_via_fp64(x):
 
 
 _ORIG_FFT = orc.FFT
+_ORIG_INR_FORWARD = orc.NetworkWithInputEncoding.forward
+
+
+def _inr_forward_via_fp64(self, x):
+    """Same network, every layer's matmul evaluated in float64 and rounded once to fp32: the
+    rounding-only perturbation an implementation with a different accumulation order (tensor cores,
+    another BLAS) applies to the MLPs."""
+    w, table = self.split()
+    h = orc.hashgrid_encode(x.float(), table, self.levels)
+    for wi in w[:-1]:
+        h = self.act((h.double() @ wi.double().t()).float())
+    return (h.double() @ w[-1].double().t()).float()[:, : self.n_output_dims]
 
 
 def loop_golden(ref_immoco, tag, h, n_mov, seed, iters, out_dir, check_restatement=True,
@@ -195,14 +207,16 @@ def loop_golden(ref_immoco, tag, h, n_mov, seed, iters, out_dir, check_restateme
     met_in = orc.crop_metrics(orc.IFFT(case["kspace_motion"]).abs(), gt)
     met_out = orc.crop_metrics(im_fin.detach().abs(), gt)
     print(f"  {tag}: corrupted {met_in} -> corrected {met_out}")
-    # drift band: the oracle loop with an fp64-evaluated FFT (same maths, other rounding)
+    # drift band: the oracle loop with fp64-evaluated FFTs and MLP matmuls (same maths, other rounding)
     orc.FFT = _fft_via_fp64
+    orc.NetworkWithInputEncoding.forward = _inr_forward_via_fp64
     try:
         im_p, _, tr_p = orc.imcoco_motion_correction(
             case["kspace_motion"], masks, iters=iters, image_params=p_img, motion_params=p_mot,
             return_trace=True)
     finally:
         orc.FFT = _ORIG_FFT
+        orc.NetworkWithInputEncoding.forward = _ORIG_INR_FORWARD
     met_p = orc.crop_metrics(im_p.detach().abs(), gt)
     rel = [abs(a - b) / abs(a) for a, b in zip(trace, tr_p)]
     print(f"  {tag}: rounding-drift band: max rel loss diff its<10 {max(rel[:10]):.2e}, "

@@ -64,9 +64,21 @@ def test_hashgrid_forward_and_backward(native_lib, dims, kind):
     assert bool((grad[untouched] == 0).all())
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "simt"])
 @pytest.mark.parametrize("width,act", [(256, "relu"), (64, "tanh"), (64, "relu"), (256, "tanh")])
 @pytest.mark.parametrize("n", [1, 127, 128, 1000, 40000])
-def test_mlp_forward_and_backward(native_lib, width, act, n):
+def test_mlp_forward_and_backward(native_lib, width, act, n, impl):
+    """impl 1 = tcgen05 kind::tf32 with the 3xTF32 split (product path), 0 = fp32 SIMT check kernels;
+    both must meet the same fp32 tolerances against torch fp32."""
+    assert native_lib.immoco_get_mlp_impl() == 1          # the product default is the tensor-core path
+    native_lib.immoco_set_mlp_impl(impl)
+    try:
+        _mlp_case(native_lib, width, act, n)
+    finally:
+        native_lib.immoco_set_mlp_impl(1)
+
+
+def _mlp_case(native_lib, width, act, n):
     g = torch.Generator().manual_seed(width + n)
     enc = (torch.randn(16, n, 2, generator=g) * 0.5).to(DEV)
     w1 = (torch.randn(width, 32, generator=g) * 0.2).to(DEV).requires_grad_(True)

@@ -95,19 +95,40 @@ def test_one_iteration_gradients_match_autograd(h, w, n_mov):
             mdl.motion_inr.params[3072:] *= 300.0
     k_in = case["kspace_motion"].to(DEV)
     k_in = k_in / k_in.abs().max() * 16000
-    losses = []
-    for mdl, ge in ((ours, mb.GradientEntropyLoss()), (theirs, orc.GradientEntropyLoss())):
+    def run(mdl, ge):
         k, im = mdl()
         loss = F.mse_loss(torch.view_as_real(k), torch.view_as_real(k_in)) + ge(im).mul(1e-2)
         loss.backward()
-        losses.append(float(loss))
+        return float(loss)
+
+    losses = [run(ours, mb.GradientEntropyLoss()), run(theirs, orc.GradientEntropyLoss())]
     assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[1])
+    # Conditioning of the motion-INR gradient: it is built from DIFFERENCES of neighbouring pixels of a
+    # nearly flat image, so rounding-level changes of the forward image move it a lot.  Measure that on
+    # the oracle itself (image perturbed by ~2 fp32 ulp) and allow a small multiple of it.
+    _, _, _, theirs_p, _, _ = _models(h, w, n_mov, 7)
+    with torch.no_grad():
+        theirs_p.motion_inr.params.copy_(theirs.motion_inr.params)
+    clean_image = theirs_p.image
+    g = torch.Generator(device=DEV).manual_seed(0)
+
+    def noisy_image():
+        img = clean_image()
+        return img * (1.0 + 2.4e-7 * torch.randn(img.shape, device=DEV, generator=g))
+
+    theirs_p.image = noisy_image
+    run(theirs_p, orc.GradientEntropyLoss())
+    sens = rel_l2(theirs_p.motion_inr.params.grad, theirs.motion_inr.params.grad)
+    print(f"motion-INR gradient sensitivity to a 2-ulp image perturbation (oracle vs oracle): {sens:.2e}")
     for name in ("image_inr", "motion_inr"):
         ga = getattr(ours, name).params.grad
         gb = getattr(theirs, name).params.grad
         n_mlp = getattr(ours, name).mlp.n_params
-        assert rel_l2(ga[:n_mlp], gb[:n_mlp]) < 2e-4, name
-        assert rel_l2(ga[n_mlp:], gb[n_mlp:]) < 2e-4, name
+        tol = 2e-4 + (5.0 * sens if name == "motion_inr" else 0.0)
+        err_mlp, err_tab = rel_l2(ga[:n_mlp], gb[:n_mlp]), rel_l2(ga[n_mlp:], gb[n_mlp:])
+        print(f"{name}: mlp grad rel {err_mlp:.2e}, table grad rel {err_tab:.2e} (tol {tol:.2e})")
+        assert err_mlp < tol, name
+        assert err_tab < tol, name
 
 
 def test_engine_equals_module_mode_for_three_steps():
