@@ -106,7 +106,7 @@ def algorithmic_bytes(slot: str, p: int, m: int, n_par: int, t_img: int, t_mot: 
     un-fused round-1 kernels still round-trip)."""
     mp = m * p
     table = {
-        "adam": 28.0 * n_par,
+        "adam_motion": 28.0 * n_par[0], "adam_image": 28.0 * n_par[1],
         "hashgrid_fwd_image": 8.0 * t_img + 8.0 * p + 128.0 * p,
         "hashgrid_bwd_image": 8.0 * t_img + 8.0 * p + 128.0 * p,
         "hashgrid_fwd_motion": 8.0 * t_mot + 12.0 * mp + 128.0 * mp,
@@ -241,12 +241,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
     p = H * W
-    n_par = models[0].image_inr.n_params + models[0].motion_inr.n_params
+    n_par2 = (models[0].motion_inr.n_params, models[0].image_inr.n_params)
+    n_par = sum(n_par2)
     per_slot = {s: (ms_sum[k] / n_prof if n_prof else 0.0) for k, s in enumerate(nat.PROFILE_SLOTS)}
     iter_ms = sum(per_slot.values())
-    dom = max(per_slot, key=per_slot.get) if n_prof else "adam"
+    dom = max(per_slot, key=per_slot.get) if n_prof else "adam_motion"
     peak, peak_src = measured_peak_gbs()
-    dom_bytes = algorithmic_bytes(dom, p, N_MOV, n_par, T_IMG_320, T_MOT_320[N_MOV])
+    dom_bytes = algorithmic_bytes(dom, p, N_MOV, n_par2, T_IMG_320, T_MOT_320[N_MOV])
     achieved = dom_bytes / (per_slot[dom] * 1e-3) / 1e9 if per_slot.get(dom) else 0.0
     traffic = None
     try:

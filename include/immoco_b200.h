@@ -70,6 +70,12 @@ int immoco_hashgrid_fwd_levels(const immoco_grid_desc* grid, const float* coords
 int immoco_hashgrid_bwd_levels(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
                                float* grad_table, int64_t n_points, int32_t level_begin,
                                int32_t level_end, void* stream);
+/* Kernel selection for A/B checks: 1 = lane-pair kernels (two adjacent lanes take the two dim-0
+ * corners of one point; product path), 0 = one thread per (point, level). Same results to rounding. */
+int immoco_set_hashgrid_impl(int32_t pair);
+/* > 0: run the lane-pair kernels as persistent grids of this many 256-thread CTAs per SM (caps their
+ * SM share when co-running); 0 (default): one CTA per (level, 128-point tile), hardware-balanced. */
+int immoco_set_hashgrid_ctas_per_sm(int32_t ctas);
 
 /* ---- (2) INR MLP: replaces the network half of tcnn.NetworkWithInputEncoding
  *          (configs at src/models/immoco.py:11-25).  One hidden layer of `width` (64 or 256),
@@ -123,6 +129,9 @@ int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc, 
 int immoco_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                      double lr, double beta1, double beta2, double eps, int32_t step,
                      int32_t zero_grad, void* stream);
+/* tuning knobs of the Adam kernel (tools/adam_bench.py): variant 0..5 = {1,2,4 items per thread} x
+ * {plain, streaming cache hints}; resident 256-thread CTAs per SM. Results are identical. */
+int immoco_set_adam_tuning(int32_t variant, int32_t ctas_per_sm);
 
 /* ---- (8) composite: iterations [it_begin, it_end) of the optimisation loop
  *          (src/models/immoco.py:164-181) on caller-provided buffers. ---------------------- */
@@ -153,12 +162,17 @@ typedef struct immoco_fit {
  * with it % profile_every == profile_every - 1 (prof may be NULL).  Slot order:
  * 0 hashgrid_fwd_image, 1 mlp_fwd_image, 2 hashgrid_fwd_motion, 3 mlp_fwd_motion, 4 fft_rows,
  * 5 motion_rows_fwd, 6 colpass_loss, 7 grad_entropy, 8 fft_rows_adj, 9 motion_rows_bwd,
- * 10 mlp_bwd_motion, 11 hashgrid_bwd_motion, 12 mlp_bwd_image, 13 hashgrid_bwd_image, 14 adam. */
-#define IMMOCO_PROFILE_SLOTS 15
+ * 10 mlp_bwd_motion, 11 hashgrid_bwd_motion, 12 mlp_bwd_image, 13 hashgrid_bwd_image, 14 adam_motion,
+ * 15 adam_image. */
+#define IMMOCO_PROFILE_SLOTS 16
 typedef struct immoco_profile immoco_profile;
 immoco_profile* immoco_profile_create(int32_t capacity);
 void immoco_profile_destroy(immoco_profile* prof);
 int immoco_profile_read(immoco_profile* prof, float* ms_sum);
+/* begin / end (ms after the iteration's first event) of every slot of instrumented iteration
+ * `index`: a two-stream timeline when immoco_set_profile_overlap(1) is in force. */
+int immoco_profile_timeline(immoco_profile* prof, int32_t index, float* begin_ms, float* end_ms);
+int immoco_set_profile_overlap(int32_t on);
 
 int immoco_fit_run(const immoco_fit* fit, int32_t it_begin, int32_t it_end,
                    const float* lambdas_host, void* stream, immoco_profile* prof,

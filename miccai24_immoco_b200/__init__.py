@@ -14,6 +14,7 @@ from ._native import build, lib, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
 from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_config,  # noqa: F401
                      imcoco_motion_correction, lambda_schedule, make_grids, mot_network_config,
                      network_config)
+from .batch import reconstruct_batch  # noqa: F401
 from .motion_utils import extract_movement_groups, lines_from_mask  # noqa: F401
 from .ops import FFT, IFFT, GradientEntropyLoss, NetworkWithInputEncoding  # noqa: F401
 from .sharding import gather_images, reconstruct_slices, shard_indices  # noqa: F401
@@ -22,5 +23,6 @@ __all__ = [
     "imcoco_motion_correction", "IMMoCo", "make_grids", "network_config", "mot_network_config",
     "encoding_config", "ClearCache", "NetworkWithInputEncoding", "FFT", "IFFT",
     "GradientEntropyLoss", "extract_movement_groups", "lines_from_mask", "FitEngine",
-    "LineStructure", "lambda_schedule", "build", "lib",
+    "LineStructure", "lambda_schedule", "build", "lib", "reconstruct_batch", "reconstruct_slices",
+    "gather_images", "shard_indices",
 ]

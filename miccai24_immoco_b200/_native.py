@@ -20,7 +20,8 @@ ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 ERR_BAD_ARG, ERR_UNSUPPORTED = -1, -2
 PROFILE_SLOTS = ["hashgrid_fwd_image", "mlp_fwd_image", "hashgrid_fwd_motion", "mlp_fwd_motion", "fft_rows",
                  "motion_rows_fwd", "colpass_loss", "grad_entropy", "fft_rows_adj", "motion_rows_bwd",
-                 "mlp_bwd_motion", "hashgrid_bwd_motion", "mlp_bwd_image", "hashgrid_bwd_image", "adam"]
+                 "mlp_bwd_motion", "hashgrid_bwd_motion", "mlp_bwd_image", "hashgrid_bwd_image", "adam_motion",
+                 "adam_image"]
 
 
 class GridDesc(C.Structure):
@@ -79,6 +80,9 @@ _SIGNATURES = {
     "immoco_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "immoco_tanh_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "immoco_set_mlp_impl": (C.c_int, [C.c_int32]),
+    "immoco_set_hashgrid_impl": (C.c_int, [C.c_int32]),
+    "immoco_set_hashgrid_ctas_per_sm": (C.c_int, [C.c_int32]),
+    "immoco_set_adam_tuning": (C.c_int, [C.c_int32, C.c_int32]),
     "immoco_get_mlp_impl": (C.c_int, []),
     "immoco_fft2c": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32,
                                C.c_float, _P]),
@@ -95,6 +99,8 @@ _SIGNATURES = {
     "immoco_profile_create": (_P, [C.c_int32]),
     "immoco_profile_destroy": (None, [_P]),
     "immoco_profile_read": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "immoco_profile_timeline": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "immoco_set_profile_overlap": (C.c_int, [C.c_int32]),
     "immoco_set_branch_overlap": (C.c_int, [C.c_int32]),
     "immoco_abi_version": (C.c_int, []),
     "immoco_launches_per_iteration": (C.c_int, [C.c_int32]),

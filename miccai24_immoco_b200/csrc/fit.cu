@@ -2,6 +2,8 @@
 // (src/models/immoco.py:149-154 optimizer, :164-181 loop).
 #include <math.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 // launch helpers implemented in forward_model.cu
@@ -19,24 +21,51 @@ namespace {
 // torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False), single-tensor formulation:
 //   m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
 // One pass: reads p,g,m,v, writes p,m,v and zeroes g (28 B / parameter), 128-bit accesses.
-__global__ void __launch_bounds__(256)
-adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
-            float4* __restrict__ v, int64_t n4, float one_minus_b1, float b2, float one_minus_b2,
-            float step_size, float bc2_sqrt, float eps, int zero_grad) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 gi = g[i];
-    float4 mi = m[i], vi = v[i], pi = p[i];
 #define IMMOCO_ADAM_LANE(c)                                              \
   mi.c = mi.c + one_minus_b1 * (gi.c - mi.c);                            \
   vi.c = fmaf(one_minus_b2 * gi.c, gi.c, b2 * vi.c);                     \
   pi.c = pi.c - step_size * (mi.c / (sqrtf(vi.c) / bc2_sqrt + eps));
-    IMMOCO_ADAM_LANE(x) IMMOCO_ADAM_LANE(y) IMMOCO_ADAM_LANE(z) IMMOCO_ADAM_LANE(w)
-#undef IMMOCO_ADAM_LANE
-    m[i] = mi; v[i] = vi; p[i] = pi;
-    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+// U independent 128-bit items per thread per trip: all 4*U loads are issued before the first use so
+// 64*U bytes per thread are in flight.  HINTS: gradients and moments are touched once per iteration
+// -> streaming (evict-first) loads/stores; the parameters are written with the default policy so the
+// tables can still be L2-resident when the next iteration's hash-grid gathers start.
+template <int U, bool HINTS>
+__global__ void __launch_bounds__(256)
+adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+            float4* __restrict__ v, int64_t n4, float one_minus_b1, float b2, float one_minus_b2,
+            float step_size, float bc2_sqrt, float eps, int zero_grad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 ga[U], ma[U], va[U], pa[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        if (HINTS) { ga[u] = __ldcs(g + i); ma[u] = __ldcs(m + i); va[u] = __ldcs(v + i); }
+        else { ga[u] = g[i]; ma[u] = m[i]; va[u] = v[i]; }
+        pa[u] = p[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        const float4 gi = ga[u];
+        float4 mi = ma[u], vi = va[u], pi = pa[u];
+        IMMOCO_ADAM_LANE(x) IMMOCO_ADAM_LANE(y) IMMOCO_ADAM_LANE(z) IMMOCO_ADAM_LANE(w)
+        if (HINTS) { __stcs(m + i, mi); __stcs(v + i, vi); }
+        else { m[i] = mi; v[i] = vi; }
+        p[i] = pi;
+        if (zero_grad) {
+          if (HINTS) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+          else g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
   }
 }
+#undef IMMOCO_ADAM_LANE
 
 __global__ void adam_tail_kernel(float* p, float* g, float* m, float* v, int64_t begin, int64_t n,
                                  float one_minus_b1, float b2, float one_minus_b2, float step_size,
@@ -53,6 +82,15 @@ __global__ void adam_tail_kernel(float* p, float* g, float* m, float* v, int64_t
 }
 
 }  // namespace
+
+static int g_adam_variant = 0, g_adam_ctas_per_sm = 32;
+// tuning knobs (tools/adam_bench.py): variant = {U=1,2,4} x {plain, streaming hints}; CTAs per SM
+extern "C" int immoco_set_adam_tuning(int32_t variant, int32_t ctas_per_sm) {
+  if (variant < 0 || variant > 5 || ctas_per_sm < 1 || ctas_per_sm > 64) return IMMOCO_ERR_BAD_ARG;
+  g_adam_variant = variant;
+  g_adam_ctas_per_sm = ctas_per_sm;
+  return 0;
+}
 
 extern "C" int immoco_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                                 int64_t n, double lr, double beta1, double beta2, double eps,
@@ -72,11 +110,21 @@ extern "C" int immoco_adam_step(float* params, float* grads, float* exp_avg, flo
   const int64_t n4 = n / 4;
   if (n4 > 0) {
     int64_t blocks = (n4 + 255) / 256;
-    const int64_t cap = (int64_t)IMMOCO_NUM_SMS * 16;   // 16 resident 256-thread CTAs per SM
+    const int64_t cap = (int64_t)IMMOCO_NUM_SMS * g_adam_ctas_per_sm;
     if (blocks > cap) blocks = cap;
-    adam_kernel<<<(unsigned)blocks, 256, 0, s>>>((float4*)params, (float4*)grads, (float4*)exp_avg,
-                                                 (float4*)exp_avg_sq, n4, omb1, (float)beta2, omb2, step_size,
-                                                 bc2_sqrt, (float)eps, zero_grad);
+#define IMMOCO_ADAM_LAUNCH(U, H)                                                                          \
+  adam_kernel<U, H><<<(unsigned)blocks, 256, 0, s>>>((float4*)params, (float4*)grads, (float4*)exp_avg,   \
+                                                     (float4*)exp_avg_sq, n4, omb1, (float)beta2, omb2,   \
+                                                     step_size, bc2_sqrt, (float)eps, zero_grad)
+    switch (g_adam_variant) {
+      case 0: IMMOCO_ADAM_LAUNCH(1, false); break;
+      case 1: IMMOCO_ADAM_LAUNCH(2, false); break;
+      case 2: IMMOCO_ADAM_LAUNCH(4, false); break;
+      case 3: IMMOCO_ADAM_LAUNCH(1, true); break;
+      case 4: IMMOCO_ADAM_LAUNCH(2, true); break;
+      default: IMMOCO_ADAM_LAUNCH(4, true); break;
+    }
+#undef IMMOCO_ADAM_LAUNCH
     IMMOCO_LAUNCH_CHECK();
   }
   if (n4 * 4 < n) {
@@ -96,8 +144,8 @@ extern "C" void immoco_struct_sizes(int32_t out[3]) {
 }
 
 // hashgrid fwd + mlp fwd (x2), rows, motion rows, colpass, GE, rows adj, motion rows bwd,
-// mlp bwd + hashgrid bwd (x2), adam
-extern "C" int immoco_launches_per_iteration(int32_t m) { return m > 0 ? 15 : 9; }
+// mlp bwd + hashgrid bwd (dense levels + hashed levels: 2 launches) (x2), adam (x2: motion, image)
+extern "C" int immoco_launches_per_iteration(int32_t m) { return m > 0 ? 18 : 10; }
 
 #define IMMOCO_TRY(expr)          \
   do {                            \
@@ -105,14 +153,16 @@ extern "C" int immoco_launches_per_iteration(int32_t m) { return m > 0 ? 15 : 9;
     if (e__ != 0) return e__;     \
   } while (0)
 
-// ---- optional per-kernel timing: CUDA events recorded on the launching stream around every
-//      kernel of selected iterations; no synchronisation until immoco_profile_read() -----------
+// ---- optional per-kernel timing: a begin and an end CUDA event around every kernel of selected
+//      iterations, recorded on the stream the kernel is launched on; nothing synchronises until
+//      immoco_profile_read() / immoco_profile_timeline() ------------------------------------------
 struct immoco_profile {
   int n_slots;                 // kernels per iteration
   int capacity;                // instrumented iterations the event pool holds
   int used;
-  cudaEvent_t* ev;             // capacity * (n_slots + 1) events
+  cudaEvent_t* ev;             // capacity * (2 * n_slots + 1) events: base, then (begin, end) per slot
 };
+static inline int prof_stride(const immoco_profile* p) { return 2 * p->n_slots + 1; }
 
 extern "C" immoco_profile* immoco_profile_create(int32_t capacity) {
   if (capacity < 1) return nullptr;
@@ -120,7 +170,7 @@ extern "C" immoco_profile* immoco_profile_create(int32_t capacity) {
   p->n_slots = IMMOCO_PROFILE_SLOTS;
   p->capacity = capacity;
   p->used = 0;
-  const int n = capacity * (p->n_slots + 1);
+  const int n = capacity * prof_stride(p);
   p->ev = new cudaEvent_t[n];
   for (int i = 0; i < n; ++i) {
     if (cudaEventCreate(&p->ev[i]) != cudaSuccess) { p->capacity = 0; break; }
@@ -130,21 +180,22 @@ extern "C" immoco_profile* immoco_profile_create(int32_t capacity) {
 
 extern "C" void immoco_profile_destroy(immoco_profile* p) {
   if (!p) return;
-  for (int i = 0; i < p->capacity * (p->n_slots + 1); ++i) cudaEventDestroy(p->ev[i]);
+  for (int i = 0; i < p->capacity * prof_stride(p); ++i) cudaEventDestroy(p->ev[i]);
   delete[] p->ev;
   delete p;
 }
 
 // Sums per-slot milliseconds over the instrumented iterations into ms_sum[IMMOCO_PROFILE_SLOTS];
 // returns the number of iterations summed (the caller must have synchronised the stream).
+// Slots that launched nothing in an iteration (n_M = 0) were still bracketed by their two events.
 extern "C" int immoco_profile_read(immoco_profile* p, float* ms_sum) {
   if (!p || !ms_sum) return IMMOCO_ERR_BAD_ARG;
   for (int k = 0; k < p->n_slots; ++k) ms_sum[k] = 0.f;
   for (int i = 0; i < p->used; ++i) {
-    cudaEvent_t* e = p->ev + (size_t)i * (p->n_slots + 1);
+    cudaEvent_t* e = p->ev + (size_t)i * prof_stride(p) + 1;
     for (int k = 0; k < p->n_slots; ++k) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, e[k], e[k + 1]) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+      if (cudaEventElapsedTime(&ms, e[2 * k], e[2 * k + 1]) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
       ms_sum[k] += ms;
     }
   }
@@ -153,38 +204,71 @@ extern "C" int immoco_profile_read(immoco_profile* p, float* ms_sum) {
   return n;
 }
 
+// begin / end of every slot of instrumented iteration `index`, in ms after that iteration's first
+// event (a timeline across both streams); does not consume the samples.
+extern "C" int immoco_profile_timeline(immoco_profile* p, int32_t index, float* begin_ms, float* end_ms) {
+  if (!p || !begin_ms || !end_ms || index < 0 || index >= p->used) return IMMOCO_ERR_BAD_ARG;
+  cudaEvent_t* base = p->ev + (size_t)index * prof_stride(p);
+  for (int k = 0; k < p->n_slots; ++k) {
+    if (cudaEventElapsedTime(&begin_ms[k], base[0], base[1 + 2 * k]) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+    if (cudaEventElapsedTime(&end_ms[k], base[0], base[2 + 2 * k]) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
 // ---- image-INR branch on a second stream --------------------------------------------------------
 // The two INR branches of an iteration are independent and stress different units
-// (hash-grid gathers / reductions: L2; MLPs: tensor pipe + SIMT epilogue), so the image branch runs on
-// an auxiliary non-blocking stream, forked and joined with events.  One aux stream + 4 events per
-// device are created on first use and live for the process (the library's only hidden state).
+// (hash-grid gathers / reductions: L2; MLPs: tensor pipe + SIMT epilogue; Adam: HBM).  The image
+// branch runs on an auxiliary non-blocking stream.  Schedule of one iteration (=> same-stream order,
+// -> event dependency):
+//   aux : [Adam_i(it-1)] => HGi_f => MLPi_f => GE  ........................  MLPi_b => HGi_b => Adam_i
+//   main: [Adam_m(it-1)] => HGm_f => MLPm_f =>(join_fwd)=> rows => motion_rows => colpass => rows_adj
+//          => motion_rows_bwd => MLPm_b =>(mlp_done -> aux)=> HGm_b => Adam_m
+// MLPi_b is released only after MLPm_b: both want every SM's tensor memory, and the motion chain is
+// the critical path.  The whole image branch (bwd of iteration it, update, fwd of it+1) then hides
+// behind HGm_b / Adam_m / HGm_f of the motion chain.
+// One aux stream + its events per (device, caller stream) are created on first use and live for the
+// process (the library's only hidden state), so concurrent fits on different streams do not share.
 struct AuxStream {
+  int dev = -1;
+  cudaStream_t owner = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork_fwd = nullptr, join_fwd = nullptr, fork_bwd = nullptr, join_bwd = nullptr;
-  bool ok = false;
+  cudaEvent_t fork = nullptr, join_fwd = nullptr, mlp_done = nullptr, join_end = nullptr;
 };
-static AuxStream* aux_for_current_device() {
-  static AuxStream table[64];
+static std::mutex g_aux_mutex;
+static AuxStream* aux_for(cudaStream_t owner) {
+  static AuxStream table[256];
+  static int used = 0;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  AuxStream& a = table[dev];
-  if (!a.ok) {
-    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEvent_t* ev[4] = {&a.fork_fwd, &a.join_fwd, &a.fork_bwd, &a.join_bwd};
-    for (auto e : ev)
-      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    a.ok = true;
-  }
-  return &a;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_aux_mutex);
+  for (int i = 0; i < used; ++i)
+    if (table[i].dev == dev && table[i].owner == owner) return &table[i];
+  if (used >= 256) return nullptr;
+  AuxStream a;
+  a.dev = dev;
+  a.owner = owner;
+  if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  cudaEvent_t* ev[4] = {&a.fork, &a.join_fwd, &a.mlp_done, &a.join_end};
+  for (auto e : ev)
+    if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  table[used] = a;
+  return &table[used++];
 }
-static int g_overlap = 1;
+static int g_overlap = 1, g_profile_overlap = 0;
 extern "C" int immoco_set_branch_overlap(int32_t on) { g_overlap = on ? 1 : 0; return 0; }
+// 1: instrumented iterations keep the two-stream schedule (timeline mode); 0 (default): they run
+// serially on the caller's stream so per-kernel durations are contention-free.
+extern "C" int immoco_set_profile_overlap(int32_t on) { g_profile_overlap = on ? 1 : 0; return 0; }
 
-#define IMMOCO_MARK()                                                  \
-  do {                                                                 \
-    if (ev) { cudaEventRecord(ev[slot], (cudaStream_t)stream); }       \
-    ++slot;                                                            \
+// K(slot, stream, launch-expression): brackets the launch(es) of one profile slot with its events
+#define K(slot, strm, expr)                                                     \
+  do {                                                                          \
+    if (ev) cudaEventRecord(ev[1 + 2 * (slot)], (cudaStream_t)(strm));          \
+    IMMOCO_TRY(expr);                                                           \
+    if (ev) cudaEventRecord(ev[2 + 2 * (slot)], (cudaStream_t)(strm));          \
   } while (0)
+static inline int nop() { return 0; }
 
 extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_end,
                               const float* lambdas_host, void* stream, immoco_profile* prof,
@@ -192,6 +276,7 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
   if (!f || !lambdas_host || it_begin < 0 || it_end < it_begin) return IMMOCO_ERR_BAD_ARG;
   const int H = f->h, W = f->w, M = f->m;
   if (H < 2 || W < 2 || M < 0 || M != f->lines.n_groups) return IMMOCO_ERR_BAD_ARG;
+  if (it_begin == it_end) return 0;
   const int64_t P = (int64_t)H * W, MP = P * M;
   const int wi = f->width_image, wm = f->width_motion;
   // parameter views: [motion | image], each [W1 (width x 32) | W2 (16 x width) | table]
@@ -201,70 +286,64 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
   float* gi = f->grads + f->n_motion;
   const int64_t mlp_m = (int64_t)wm * 32 + 16 * (int64_t)wm;
   const int64_t mlp_i = (int64_t)wi * 32 + 16 * (int64_t)wi;
+  if ((f->n_motion & 3) != 0) return IMMOCO_ERR_BAD_ARG;   // keeps the image half 16-byte aligned
+
+  cudaStream_t ms = (cudaStream_t)stream;
+  AuxStream* aux = (g_overlap && M > 0) ? aux_for(ms) : nullptr;
+  bool forked = false;          // aux currently carries work that `ms` has not joined
 
   for (int it = it_begin; it < it_end; ++it) {
     double* loss = f->loss + 2 * (int64_t)it;
     cudaEvent_t* ev = nullptr;
     if (prof && profile_every > 0 && (it % profile_every) == profile_every - 1 && prof->used < prof->capacity)
-      ev = prof->ev + (size_t)(prof->used++) * (prof->n_slots + 1);
-    int slot = 0;
-    // instrumented iterations run serially on the caller's stream so per-kernel event times mean something
-    AuxStream* aux = (g_overlap && !ev && M > 0) ? aux_for_current_device() : nullptr;
-    cudaStream_t ms = (cudaStream_t)stream;
-    void* is = aux ? (void*)aux->stream : stream;       // stream of the image-INR branch
-    IMMOCO_MARK();
+      ev = prof->ev + (size_t)(prof->used++) * prof_stride(prof);
+    // instrumented iterations run serially on the caller's stream (contention-free durations) unless
+    // timeline mode is on
+    const bool two = aux && (!ev || g_profile_overlap);
+    if (!two && forked) {       // fold the image branch back before a serial iteration
+      cudaEventRecord(aux->join_end, aux->stream);
+      cudaStreamWaitEvent(ms, aux->join_end, 0);
+      forked = false;
+    }
+    if (two && !forked) {       // the image branch starts behind everything already on `ms`
+      cudaEventRecord(aux->fork, ms);
+      cudaStreamWaitEvent(aux->stream, aux->fork, 0);
+      forked = true;
+    }
+    void* is = two ? (void*)aux->stream : stream;       // stream of the image-INR branch
+    if (ev) cudaEventRecord(ev[0], ms);
     // ---- forward -------------------------------------------------------------------------------
-    if (aux) { cudaEventRecord(aux->fork_fwd, ms); cudaStreamWaitEvent(aux->stream, aux->fork_fwd, 0); }
-    IMMOCO_TRY(immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is));
-    IMMOCO_MARK();  // slot 0: hashgrid_fwd_image
-    IMMOCO_TRY(immoco_mlp_fwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->image, P, wi, f->act_image, 0, is));
-    IMMOCO_MARK();  // 1: mlp_fwd_image
-    if (aux) cudaEventRecord(aux->join_fwd, aux->stream);
-    if (M > 0) {
-      IMMOCO_TRY(immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream));
-    }
-    IMMOCO_MARK();  // 2: hashgrid_fwd_motion
-    if (M > 0) {
-      IMMOCO_TRY(immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream));
-    }
-    IMMOCO_MARK();  // 3: mlp_fwd_motion
-    if (aux) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
-    IMMOCO_TRY(immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
-    IMMOCO_MARK();  // 4: fft_rows
-    IMMOCO_TRY(immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
-    IMMOCO_MARK();  // 5: motion_rows_fwd
-    IMMOCO_TRY(immoco_colpass_loss(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
-    IMMOCO_MARK();  // 6: colpass_loss
+    K(0, is, immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is));
+    K(1, is, immoco_mlp_fwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->image, P, wi, f->act_image, 0, is));
+    // gradient entropy needs the image only; it initialises d_image (lambda folded in)
+    K(7, is, immoco_grad_entropy(f->image, lambdas_host[it], loss + 1, f->d_image, 0, H, W, is));
+    if (two) cudaEventRecord(aux->join_fwd, aux->stream);
+    K(2, ms, M > 0 ? immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream) : nop());
+    K(3, ms, M > 0 ? immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream) : nop());
+    if (two) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
+    K(4, ms, immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
+    K(5, ms, immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
+    K(6, ms, immoco_colpass_loss(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
     // ---- backward ------------------------------------------------------------------------------
-    IMMOCO_TRY(immoco_grad_entropy(f->image, lambdas_host[it], loss + 1, f->d_image, 0, H, W, stream));
-    IMMOCO_MARK();  // 7: grad_entropy
-    IMMOCO_TRY(immoco_rows_static(f->d_c, f->d_image, H, W, f->tw_w, f->lines.static_w, nullptr, 1, true, stream));
-    IMMOCO_MARK();  // 8: fft_rows_adj
-    if (M > 0) {
-      IMMOCO_TRY(immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
-                                        f->d_image, f->d_disp, H, W, stream));
-    }
-    IMMOCO_MARK();  // 9: motion_rows_bwd
-    if (aux) { cudaEventRecord(aux->fork_bwd, ms); cudaStreamWaitEvent(aux->stream, aux->fork_bwd, 0); }
-    if (M > 0) {
-      IMMOCO_TRY(immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
-                                gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream));
-    }
-    IMMOCO_MARK();  // 10: mlp_bwd_motion
-    if (M > 0) {
-      IMMOCO_TRY(immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream));
-    }
-    IMMOCO_MARK();  // 11: hashgrid_bwd_motion
-    IMMOCO_TRY(immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
-                              gi + (int64_t)wi * 32, P, wi, f->act_image, is));
-    IMMOCO_MARK();  // 12: mlp_bwd_image
-    IMMOCO_TRY(immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is));
-    IMMOCO_MARK();  // 13: hashgrid_bwd_image
-    if (aux) { cudaEventRecord(aux->join_bwd, aux->stream); cudaStreamWaitEvent(ms, aux->join_bwd, 0); }
-    // ---- update (zero_grad fused) ----------------------------------------------------------------
-    IMMOCO_TRY(immoco_adam_step(f->params, f->grads, f->exp_avg, f->exp_avg_sq, f->n_motion + f->n_image,
-                                f->lr, f->beta1, f->beta2, f->eps, it + 1, 1, stream));
-    IMMOCO_MARK();  // 14: adam
+    K(8, ms, immoco_rows_static(f->d_c, f->d_image, H, W, f->tw_w, f->lines.static_w, nullptr, 1, true, stream));
+    K(9, ms, M > 0 ? immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
+                                            f->d_image, f->d_disp, H, W, stream) : nop());
+    K(10, ms, M > 0 ? immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
+                                     gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream) : nop());
+    if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
+    K(11, ms, M > 0 ? immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream) : nop());
+    K(12, is, immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
+                             gi + (int64_t)wi * 32, P, wi, f->act_image, is));
+    K(13, is, immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is));
+    // ---- update (zero_grad fused), one launch per INR so each follows its own branch ---------------
+    K(14, ms, M > 0 ? immoco_adam_step(pm, gm, f->exp_avg, f->exp_avg_sq, f->n_motion, f->lr, f->beta1, f->beta2,
+                                       f->eps, it + 1, 1, stream) : nop());
+    K(15, is, immoco_adam_step(pi, gi, f->exp_avg + f->n_motion, f->exp_avg_sq + f->n_motion, f->n_image, f->lr,
+                               f->beta1, f->beta2, f->eps, it + 1, 1, is));
+  }
+  if (forked) {
+    cudaEventRecord(aux->join_end, aux->stream);
+    cudaStreamWaitEvent(ms, aux->join_end, 0);
   }
   return 0;
 }

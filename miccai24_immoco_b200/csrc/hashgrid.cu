@@ -116,6 +116,164 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
   }
 }
 
+
+// ---- lane-pair kernels -----------------------------------------------------------------------
+// The first input dimension carries hash prime 1, so the two corners q0 / q0+1 of that dimension sit
+// in rows idx and idx ^ (2^k - 1): the same 128-byte line 15 times out of 16 (the same 32-byte sector
+// half of the time).  Two ADJACENT LANES therefore take the two dim-0 corners of one point: every
+// gather / reduction instruction of a warp touches 16 lines instead of 32, which is what the L1TEX
+// tag stage (1 line per cycle per SM) and the L2 atomic units are paced by.  The partial sums of a
+// lane pair are combined with one shuffle.
+constexpr int kPairPoints = kThreads / 2;
+
+// Index arithmetic specialised per level kind (uniform per CTA item, so the branch is free):
+//   HASH : idx = (q0 ^ q1*P1 ^ q2*P2) & (entries-1)      entries a power of two
+//   DENSE: idx = (q0 + q1*res + q2*res^2) & (entries-1)  entries a power of two
+//   ANY  : grid_index() with its general modulo (odd resolutions, non-power-of-two tables)
+// The per-dimension terms are computed once per point; a corner costs one or two XOR/ADDs and an AND.
+enum { kIdxHash = 0, kIdxDense = 1, kIdxAny = 2 };
+
+template <int D, int MODE>
+struct PairTerms {
+  uint32_t t[D][2];     // t[d][bit]: contribution of corner bit `bit` of dimension d (d >= 1)
+  uint32_t q0, mask, entries, res, hashed;
+  uint32_t cell[D];
+  __device__ __forceinline__ void init(const uint32_t (&c)[D], int half, uint32_t entries_, uint32_t res_,
+                                       uint32_t hashed_) {
+    entries = entries_; res = res_; hashed = hashed_; mask = entries_ - 1u;
+    q0 = c[0] + (uint32_t)half;
+    uint32_t mul = 1u;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      cell[d] = c[d];
+      if (MODE == kIdxHash) mul = (d == 0) ? 1u : (d == 1 ? 2654435761u : 805459861u);
+      t[d][0] = c[d] * mul;
+      t[d][1] = (c[d] + 1u) * mul;
+      if (MODE == kIdxDense) mul *= res_;
+    }
+  }
+  // corner bits of dimensions 1.. in `c` (bit d-1 = dimension d); dimension 0 is this lane's half
+  __device__ __forceinline__ uint32_t index(int c) const {
+    if (MODE == kIdxAny) {
+      uint32_t q[D];
+      q[0] = q0;
+#pragma unroll
+      for (int d = 1; d < D; ++d) q[d] = cell[d] + (uint32_t)((c >> (d - 1)) & 1);
+      return grid_index<D>(q, hashed, entries, res);
+    }
+    uint32_t idx = q0;      // prime 1 / stride 1
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const uint32_t term = t[d][(c >> (d - 1)) & 1];
+      idx = (MODE == kIdxHash) ? (idx ^ term) : (idx + term);
+    }
+    return idx & mask;
+  }
+};
+
+template <int D>
+__device__ __forceinline__ float pair_weight(const float (&frac)[D], float w0, int c) {
+  float w = w0;
+#pragma unroll
+  for (int d = 1; d < D; ++d) w = w * (((c >> (d - 1)) & 1) ? frac[d] : 1.0f - frac[d]);   // (w0 * w1) * w2
+  return w;
+}
+
+template <int D, int MODE>
+__device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, const float2* __restrict__ tab,
+                                              float2* __restrict__ enc_level, int n, int base, float scale,
+                                              uint32_t res, uint32_t entries, uint32_t hashed) {
+  const int half = threadIdx.x & 1;
+  const int i = base + (threadIdx.x >> 1);
+  float2 acc = make_float2(0.f, 0.f);
+  if (i < n) {
+    uint32_t cell[D];
+    float frac[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+    PairTerms<D, MODE> pt;
+    pt.init(cell, half, entries, res, hashed);
+    const float w0 = half ? frac[0] : 1.0f - frac[0];
+    float2 v[1 << (D - 1)];
+#pragma unroll
+    for (int c = 0; c < (1 << (D - 1)); ++c) v[c] = __ldg(tab + pt.index(c));     // all gathers in flight
+#pragma unroll
+    for (int c = 0; c < (1 << (D - 1)); ++c) {
+      const float w = pair_weight<D>(frac, w0, c);
+      acc.x = fmaf(w, v[c].x, acc.x);
+      acc.y = fmaf(w, v[c].y, acc.y);
+    }
+  }
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+  acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+  if (i < n && half == 0) enc_level[i] = acc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+hashgrid_fwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                         const float2* __restrict__ table, float2* __restrict__ enc, int n, int level0,
+                         int n_levels, int tiles) {
+  // CTAs walk (level, tile) items in level-major order: one level's table (<= 4 MB) is the L2 working
+  // set at any time; with a capped grid (immoco_set_hashgrid_ctas_per_sm) the CTAs are persistent
+  for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
+    const int level = level0 + item / tiles;
+    const int base = (item % tiles) * kPairPoints;
+    const float scale = g.scale[level];
+    const uint32_t res = g.resolution[level];
+    const uint32_t entries = g.entries[level];
+    const uint32_t hashed = g.hashed[level];
+    const float2* __restrict__ tab = table + g.offset[level];
+    float2* __restrict__ out = enc + (size_t)level * n;
+    const bool pow2 = (entries & (entries - 1u)) == 0u;
+    if (pow2 && hashed) fwd_pair_item<D, kIdxHash>(coords, tab, out, n, base, scale, res, entries, hashed);
+    else if (pow2) fwd_pair_item<D, kIdxDense>(coords, tab, out, n, base, scale, res, entries, hashed);
+    else fwd_pair_item<D, kIdxAny>(coords, tab, out, n, base, scale, res, entries, hashed);
+  }
+}
+
+template <int D, int MODE>
+__device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, const float2* __restrict__ d_enc_level,
+                                              float2* __restrict__ gtab, int n, int base, float scale,
+                                              uint32_t res, uint32_t entries) {
+  const int half = threadIdx.x & 1;
+  const int i = base + (threadIdx.x >> 1);
+  if (i >= n) return;
+  const float2 go = __ldg(d_enc_level + i);
+  if (go.x == 0.0f && go.y == 0.0f) return;              // adding +-0 is a no-op
+  uint32_t cell[D];
+  float frac[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+  PairTerms<D, MODE> pt;
+  pt.init(cell, half, entries, res, 1u);
+  const float w0 = half ? frac[0] : 1.0f - frac[0];
+#pragma unroll
+  for (int c = 0; c < (1 << (D - 1)); ++c) {
+    const float w = pair_weight<D>(frac, w0, c);
+    atomicAdd(gtab + pt.index(c), make_float2(w * go.x, w * go.y));
+  }
+}
+
+// hashed levels only (dense levels keep the run-aggregating kernel above)
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+hashgrid_bwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                         const float2* __restrict__ d_enc, float2* __restrict__ grad_table, int n, int level0,
+                         int n_levels, int tiles) {
+  for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
+    const int level = level0 + item / tiles;
+    const int base = (item % tiles) * kPairPoints;
+    const float scale = g.scale[level];
+    const uint32_t res = g.resolution[level];
+    const uint32_t entries = g.entries[level];
+    float2* __restrict__ gtab = grad_table + g.offset[level];
+    const float2* __restrict__ go = d_enc + (size_t)level * n;
+    if ((entries & (entries - 1u)) == 0u) bwd_pair_item<D, kIdxHash>(coords, go, gtab, n, base, scale, res, entries);
+    else bwd_pair_item<D, kIdxAny>(coords, go, gtab, n, base, scale, res, entries);
+  }
+}
+
 int check(const immoco_grid_desc* g, int64_t n) {
   if (!g || n < 0 || n > (int64_t)0x7fffffff / 2) return IMMOCO_ERR_BAD_ARG;
   if (g->n_levels < 1 || g->n_levels > IMMOCO_MAX_LEVELS) return IMMOCO_ERR_BAD_ARG;
@@ -125,18 +283,38 @@ int check(const immoco_grid_desc* g, int64_t n) {
 
 }  // namespace
 
+static int g_pair = 1;   // 1: lane-pair kernels (product path); 0: one thread per point (A/B check)
+static int g_ctas_per_sm = 0;   // > 0: persistent pair kernels with this many 256-thread CTAs per SM; 0: one CTA per item
+extern "C" int immoco_set_hashgrid_impl(int32_t pair) { g_pair = pair ? 1 : 0; return 0; }
+extern "C" int immoco_set_hashgrid_ctas_per_sm(int32_t ctas) {
+  if (ctas < 0 || ctas > 64) return IMMOCO_ERR_BAD_ARG;
+  g_ctas_per_sm = ctas;
+  return 0;
+}
+
 static int run_fwd(const immoco_grid_desc* grid, const float* coords, const float* table, float* enc,
                    int64_t n_points, int l0, int l1, void* stream) {
   if (int e = check(grid, n_points)) return e;
   if (l0 < 0 || l1 > grid->n_levels || l0 > l1) return IMMOCO_ERR_BAD_ARG;
   if (n_points == 0 || l0 == l1) return 0;
   const int n = (int)n_points;
-  dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(l1 - l0));
   cudaStream_t s = (cudaStream_t)stream;
-  if (grid->n_dims == 2)
-    hashgrid_fwd_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0);
-  else
-    hashgrid_fwd_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0);
+  if (g_pair) {
+    const int tiles = (int)ceil_div64(n, kPairPoints);
+    const int64_t items = (int64_t)tiles * (l1 - l0);
+    const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
+    const unsigned g = (unsigned)(items < cap ? items : cap);
+    if (grid->n_dims == 2)
+      hashgrid_fwd_pair_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0, l1 - l0, tiles);
+    else
+      hashgrid_fwd_pair_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0, l1 - l0, tiles);
+  } else {
+    dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(l1 - l0));
+    if (grid->n_dims == 2)
+      hashgrid_fwd_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0);
+    else
+      hashgrid_fwd_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0);
+  }
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
@@ -147,13 +325,31 @@ static int run_bwd(const immoco_grid_desc* grid, const float* coords, const floa
   if (l0 < 0 || l1 > grid->n_levels || l0 > l1) return IMMOCO_ERR_BAD_ARG;
   if (n_points == 0 || l0 == l1) return 0;
   const int n = (int)n_points;
-  dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(l1 - l0));
   cudaStream_t s = (cudaStream_t)stream;
-  if (grid->n_dims == 2)
-    hashgrid_bwd_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, l0);
-  else
-    hashgrid_bwd_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, l0);
-  IMMOCO_LAUNCH_CHECK();
+  // consecutive levels of one kind (dense: run-aggregating kernel, hashed: lane-pair kernel) per launch
+  for (int a = l0; a < l1;) {
+    int b = a + 1;
+    const bool pair = g_pair && grid->hashed[a];
+    while (b < l1 && (g_pair && grid->hashed[b]) == pair) ++b;
+    dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(b - a));
+    if (pair) {
+      const int tiles = (int)ceil_div64(n, kPairPoints);
+      const int64_t items = (int64_t)tiles * (b - a);
+      const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
+      const unsigned gp = (unsigned)(items < cap ? items : cap);
+      if (grid->n_dims == 2)
+        hashgrid_bwd_pair_kernel<2><<<gp, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);
+      else
+        hashgrid_bwd_pair_kernel<3><<<gp, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);
+    } else {
+      if (grid->n_dims == 2)
+        hashgrid_bwd_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a);
+      else
+        hashgrid_bwd_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a);
+    }
+    IMMOCO_LAUNCH_CHECK();
+    a = b;
+  }
   return 0;
 }
 

@@ -74,22 +74,46 @@ def _identity_grid(h: int, w: int, device) -> torch.Tensor:
     return F.affine_grid(theta, torch.Size((1, 1, h, w)), align_corners=True).to(device)
 
 
+# The coordinate buffers depend on the shape only (immoco.py:72-80 rebuilds them per instance); one
+# device copy per (shape, device) is shared by every instance: they are read-only on the data path.
+_COORD_CACHE: dict = {}
+
+
+def _cached_coords(kind: str, shape, device) -> torch.Tensor:
+    key = (kind, tuple(int(v) for v in shape), str(device))
+    t = _COORD_CACHE.get(key)
+    if t is None:
+        t = _identity_grid(shape[0], shape[1], device) if kind == "identity" else make_grids(shape, device)
+        _COORD_CACHE[key] = t
+    return t
+
+
+def _upload(array: np.ndarray, device) -> torch.Tensor:
+    """Small host array -> device through pinned memory, stream-ordered, no host synchronisation."""
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if torch.device(device).type != "cuda":
+        return t
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 class LineStructure:
     """Column structure of (M, H, W) movement-group masks, uploaded once per instance.
 
     The reference builds masks with extract_movement_groups (motion_utils.py:56-109): every mask
-    is constant along rows.  Masks that vary along rows are rejected (documented limitation)."""
+    is constant along rows.  Masks that vary along rows are rejected (documented limitation).
+    ``masks`` may live on the host (no device synchronisation at all) or on the device (one D2H)."""
 
-    def __init__(self, masks: torch.Tensor):
+    def __init__(self, masks: torch.Tensor, device=None):
         if masks.dim() != 3:
             raise ValueError("masks must have shape (num_movements, H, num_lines)")
         m, h, w = masks.shape
-        mf = masks.detach().to(torch.float32)
+        dev = masks.device if device is None else torch.device(device)
+        mf = masks.detach().to("cpu").to(torch.float32).numpy()
         if m > 0 and h > 1 and not bool((mf == mf[:, :1, :]).all()):
             raise NotImplementedError(
                 "movement-group masks must be constant along dim -2 (column indicators, as produced "
                 "by extract_movement_groups); row-varying masks are not supported by the CUDA path")
-        cols = mf[:, 0, :].cpu().numpy() if m > 0 else np.zeros((0, w), np.float32)   # (M, W)
+        cols = mf[:, 0, :] if m > 0 else np.zeros((0, w), np.float32)   # (M, W)
         ofs, idx, wt = [0], [], []
         for g in range(m):
             nz = np.nonzero(cols[g])[0]
@@ -97,12 +121,11 @@ class LineStructure:
             wt.extend(float(cols[g, v]) for v in nz)
             ofs.append(len(idx))
         static = (1.0 - cols.sum(0)).astype(np.float32) if m > 0 else np.ones(w, np.float32)
-        dev = masks.device
         self.m, self.h, self.w = m, h, w
-        self.group_ofs = torch.tensor(ofs, dtype=torch.int32, device=dev)
-        self.line_idx = torch.tensor(idx if idx else [0], dtype=torch.int32, device=dev)
-        self.line_w = torch.tensor(wt if wt else [0.0], dtype=torch.float32, device=dev)
-        self.static_w = torch.from_numpy(static).to(dev)
+        self.group_ofs = _upload(np.asarray(ofs, np.int32), dev)
+        self.line_idx = _upload(np.asarray(idx if idx else [0], np.int32), dev)
+        self.line_w = _upload(np.asarray(wt if wt else [0.0], np.float32), dev)
+        self.static_w = _upload(static, dev)
         self.max_lines = max([ofs[i + 1] - ofs[i] for i in range(m)] + [1])
         self.n_lines = len(idx)
 
@@ -165,7 +188,7 @@ class IMMoCo(nn.Module):
     Attributes kept from the reference: image_inr, motion_inr, masks, num_movements, x, num_lines,
     device, identy_grid, input_grid.  ``forward() -> (kspace_out, image_prior)``."""
 
-    def __init__(self, masks, image_seed: int = 1337, motion_seed: int = 1338):
+    def __init__(self, masks, image_seed: int = 1337, motion_seed: int = 1338, host_masks=None):
         super().__init__()
         _need_cuda(masks, "IMMoCo(masks)")
         dev = masks.device
@@ -177,9 +200,10 @@ class IMMoCo(nn.Module):
         self.masks = masks
         self.num_movements, self.x, self.num_lines = masks.shape
         self.device = dev
-        self.identy_grid = _identity_grid(self.x, self.num_lines, dev)
-        self.input_grid = make_grids((self.num_movements, self.x, self.num_lines), device=dev)
-        self._lines = LineStructure(masks)
+        self.identy_grid = _cached_coords("identity", (self.x, self.num_lines), dev)
+        self.input_grid = _cached_coords("motion", (self.num_movements, self.x, self.num_lines), dev)
+        # host_masks: the same masks still on the host (batch driver) -> no device synchronisation
+        self._lines = LineStructure(masks if host_masks is None else host_masks, device=dev)
         self._ident = self.identy_grid.view(-1, 2).contiguous()
 
     def forward(self):
@@ -214,7 +238,7 @@ def lambda_schedule(iters: int, lambda_ge: float, variant: str = "main") -> List
 
 class FitEngine:
     """Device state + native loop for ONE slice: both INRs' parameters, gradients and Adam moments
-    live in one flat fp32 vector [motion | image]; every iteration is 15 kernel launches issued by
+    live in one flat fp32 vector [motion | image]; every iteration is 18 kernel launches issued by
     ``immoco_fit_run`` with no host synchronisation."""
 
     def __init__(self, model: IMMoCo, max_iters: int):

@@ -44,18 +44,24 @@ def gather_images(local: torch.Tensor, n_slices: int, rank: int, world: int, dst
 
 def reconstruct_slices(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], *, iters: int = 200,
                        learning_rate: float = 1e-2, lambda_ge: float = 1e-2,
-                       reconstruct_fn: Optional[Callable] = None) -> Optional[torch.Tensor]:
+                       reconstruct_fn: Optional[Callable] = None, in_flight: Optional[int] = None
+                       ) -> Optional[torch.Tensor]:
     """Reconstruct every slice of a stack, sharded over the ranks of the default process group.
 
-    ``reconstruct_fn(kspace, masks, iters, learning_rate, lambda_ge, False) -> (image, kspace_fwd)``
-    defaults to the CUDA ``imcoco_motion_correction``.  All slices must share (H, W)."""
-    if reconstruct_fn is None:
-        from .immoco import imcoco_motion_correction as reconstruct_fn
+    By default each rank runs its shard through ``reconstruct_batch`` (several slices in flight per
+    GPU).  ``reconstruct_fn(kspace, masks, iters, learning_rate, lambda_ge, False) -> (image,
+    kspace_fwd)`` replaces the per-slice fit (the gloo tests inject a CPU stand-in).  All slices must
+    share (H, W)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     n = len(kspaces)
     mine = shard_indices(n, rank, world)
-    outs = [reconstruct_fn(kspaces[s], masks[s], iters, learning_rate, lambda_ge, False)[0] for s in mine]
+    if reconstruct_fn is None:
+        from .batch import DEFAULT_IN_FLIGHT, reconstruct_batch
+        outs = reconstruct_batch([kspaces[s] for s in mine], [masks[s] for s in mine], iters, learning_rate,
+                                 lambda_ge, in_flight=in_flight or DEFAULT_IN_FLIGHT) if mine else []
+    else:
+        outs = [reconstruct_fn(kspaces[s], masks[s], iters, learning_rate, lambda_ge, False)[0] for s in mine]
     if outs:
         local = torch.stack([o.detach() for o in outs])
     else:

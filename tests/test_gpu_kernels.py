@@ -38,9 +38,17 @@ def _coords(dims, kind):
     return (torch.rand(n, dims, generator=g) * 3.0 - 1.5).contiguous()       # incl. negative cells
 
 
+@pytest.fixture
+def hashgrid_impl(native_lib, request):
+    native_lib.immoco_set_hashgrid_impl(request.param)
+    yield request.param
+    native_lib.immoco_set_hashgrid_impl(1)
+
+
+@pytest.mark.parametrize("hashgrid_impl", [1, 0], ids=["lane-pair", "thread-per-point"], indirect=True)
 @pytest.mark.parametrize("dims", [2, 3])
 @pytest.mark.parametrize("kind", ["grid", "ragged", "tiny"])
-def test_hashgrid_forward_and_backward(native_lib, dims, kind):
+def test_hashgrid_forward_and_backward(native_lib, dims, kind, hashgrid_impl):
     gs = grid_spec(dims, mb.encoding_config)
     lv = orc.make_grid_levels(dims, orc.ENCODING_CONFIG)
     x = _coords(dims, kind).to(DEV)
