@@ -263,6 +263,8 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": round(per_slot[dom], 5),
         "kernel_share_of_iteration": round(per_slot[dom] / iter_ms, 4) if iter_ms else None,
         "per_kernel_ms": {k: round(v, 5) for k, v in per_slot.items()},
+        "per_kernel_gbs": {k: round(algorithmic_bytes(k, p, N_MOV, n_par2, T_IMG_320, T_MOT_320[N_MOV]) / (v * 1e-3) / 1e9, 1)
+                           for k, v in per_slot.items() if v > 0},
         "instrumented_iterations": n_prof,
         "iteration": {"algorithmic_bytes": b_iter, "achieved": round(b_iter / (ms_per_iter * 1e-3) / 1e9, 1),
                       "frac": round(b_iter / (ms_per_iter * 1e-3) / 1e9 / peak, 4)},

@@ -13,8 +13,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRowsPerCta = 4;   // row pass: transforms per CTA
-constexpr int kColsPerCta = 8;   // column pass: adjacent columns per CTA (64 B segments)
+constexpr int kRowsPerCta = 2;   // row pass: transforms per CTA
+constexpr int kColsPerCta = 4;   // column pass: adjacent columns per CTA (64 B segments)
 
 __device__ __forceinline__ int wrap_mod(int a, int n) {
   int r = a % n;
