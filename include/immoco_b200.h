@@ -181,6 +181,29 @@ int immoco_fit_run(const immoco_fit* fit, int32_t it_begin, int32_t it_end,
  * auxiliary stream, forked from / joined to `stream` with events; 0: everything on `stream`. */
 int immoco_set_branch_overlap(int32_t on);
 
+/* ---- (9) evaluation metrics on the device: replaces calmetric2D's normalize / my_psnr / piq.ssim /
+ *          rmse (src/utils/evaluate.py:19-47,57-80; caller src/test/test_immoco.py:74-85).
+ *          pred / gt: (batch, h, w) strided views (strides in elements; a complex view is read as its
+ *          magnitude).  minmax: batch*4 floats scratch.  acc: batch*4 doubles ZEROED by the caller,
+ *          receives {sum of squared error of the min-max-normalised images, sum of the SSIM map,
+ *          SSIM map size, -}.  Gaussian window sigma 1.5, kernel_size <= 11, pool = piq's
+ *          down-sampling factor max(1, round(min(h,w)/256)). -------------------------------------- */
+int immoco_metrics2d(const float* pred, int64_t pred_img_stride, int64_t pred_row_stride,
+                     int32_t pred_complex, const float* gt, int64_t gt_img_stride, int64_t gt_row_stride,
+                     int32_t gt_complex, int32_t batch, int32_t h, int32_t w, int32_t kernel_size,
+                     int32_t pool, float* minmax, double* acc, void* stream);
+
+/* ---- (10) synthetic rigid motion: the image-domain half of motion_simulation2D
+ *          (src/utils/motion_utils.py:121-202).  theta: (n_mov, 6) affine rows as handed to
+ *          F.affine_grid(align_corners=True); out: (n_mov, h, w) complex, bilinear, border padding,
+ *          sampled with align_corners=False (motion_utils.py:165-186). ------------------------------ */
+int immoco_rigid_resample(const float* image, const float* theta, float* out, int32_t n_mov, int32_t h,
+                          int32_t w, void* stream);
+/* k[:, w0[m]:w1[m]] = k_moved[m][:, w0[m]:w1[m]] for m in order; mask (int64, may be NULL) gets 1 there
+ * (motion_utils.py:188-198).  w0 / w1 are device arrays. */
+int immoco_replace_lines(float* k, const float* k_moved, int64_t* mask, const int32_t* w0, const int32_t* w1,
+                         int32_t n_mov, int32_t h, int32_t w, void* stream);
+
 /* library/ABI version and the number of kernel launches one fit iteration issues */
 int immoco_abi_version(void);
 /* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit): lets a foreign-language

@@ -15,7 +15,9 @@ from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_conf
                      imcoco_motion_correction, lambda_schedule, make_grids, mot_network_config,
                      network_config)
 from .batch import reconstruct_batch  # noqa: F401
-from .motion_utils import extract_movement_groups, lines_from_mask  # noqa: F401
+from .metrics import calmetric2D, crop_metrics, my_psnr, normalize, rmse  # noqa: F401
+from .motion_utils import (extract_movement_groups, generate_list, get_rand_int, lines_from_mask,  # noqa: F401
+                           motion_simulation2D, rotation_matrix_2d)
 from .ops import FFT, IFFT, GradientEntropyLoss, NetworkWithInputEncoding  # noqa: F401
 from .sharding import gather_images, reconstruct_slices, shard_indices  # noqa: F401
 
@@ -24,5 +26,6 @@ __all__ = [
     "encoding_config", "ClearCache", "NetworkWithInputEncoding", "FFT", "IFFT",
     "GradientEntropyLoss", "extract_movement_groups", "lines_from_mask", "FitEngine",
     "LineStructure", "lambda_schedule", "build", "lib", "reconstruct_batch", "reconstruct_slices",
-    "gather_images", "shard_indices",
+    "gather_images", "shard_indices", "calmetric2D", "crop_metrics", "my_psnr", "normalize", "rmse",
+    "motion_simulation2D", "generate_list", "get_rand_int", "rotation_matrix_2d",
 ]

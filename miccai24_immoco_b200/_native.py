@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libimmoco_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu"]
+SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu"]
 
 MAX_LEVELS = 16
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -96,6 +96,10 @@ _SIGNATURES = {
                                    C.c_double, C.c_int32, C.c_int32, _P]),
     "immoco_fit_run": (C.c_int, [C.POINTER(Fit), C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P,
                                  C.c_int32]),
+    "immoco_metrics2d": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "immoco_rigid_resample": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "immoco_replace_lines": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_profile_create": (_P, [C.c_int32]),
     "immoco_profile_destroy": (None, [_P]),
     "immoco_profile_read": (C.c_int, [_P, C.POINTER(C.c_float)]),
@@ -113,7 +117,7 @@ _lib = None
 
 def nvcc_command(out_path: str = LIB_PATH) -> List[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
             "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(_ROOT, "include"),
             "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
 
