@@ -204,6 +204,23 @@ int immoco_rigid_resample(const float* image, const float* theta, float* out, in
 int immoco_replace_lines(float* k, const float* k_moved, int64_t* mask, const int32_t* w0, const int32_t* w1,
                          int32_t n_mov, int32_t h, int32_t w, void* stream);
 
+/* ---- (11) kld-net inference: the kernels of fastmri.models.Unet (== src/models/unet.py:17-187 with
+ *          InstanceNorm2d), NCHW fp32, as used at src/test/test_immoco.py:17-20,50-58.
+ *          conv3x3: pad 1, no bias, over the channel concat [in0 (c0) | in1 (c1, may be NULL/0)];
+ *          writes the RAW output and accumulates per-(image, channel) {sum, sum of squares} into
+ *          stats (n*cout*2 doubles, ZEROED by the caller).  convt2x2: ConvTranspose2d(k=2, s=2, no
+ *          bias), weight (cin, cout, 2, 2), out (n, cout, 2h, 2w), same statistics.  instnorm_lrelu:
+ *          in place over `planes` = n*c planes, biased variance, then LeakyReLU(slope); `pooled` (may be
+ *          NULL) receives the 2x2 average pool (planes, h/2, w/2).  conv1x1: with bias (may be NULL). -- */
+int immoco_unet_conv3x3(const float* in0, int32_t c0, const float* in1, int32_t c1, const float* weight,
+                        float* out, double* stats, int32_t n, int32_t cout, int32_t h, int32_t w, void* stream);
+int immoco_unet_convt2x2(const float* in, const float* weight, float* out, double* stats, int32_t n,
+                         int32_t cin, int32_t cout, int32_t h, int32_t w, void* stream);
+int immoco_unet_instnorm_lrelu(float* x, const double* stats, float* pooled, int32_t planes, int32_t h,
+                               int32_t w, float eps, float slope, void* stream);
+int immoco_unet_conv1x1(const float* in, const float* weight, const float* bias, float* out, int32_t n,
+                        int32_t cin, int32_t cout, int32_t hw, void* stream);
+
 /* library/ABI version and the number of kernel launches one fit iteration issues */
 int immoco_abi_version(void);
 /* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit): lets a foreign-language

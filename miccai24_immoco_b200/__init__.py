@@ -15,6 +15,7 @@ from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_conf
                      imcoco_motion_correction, lambda_schedule, make_grids, mot_network_config,
                      network_config)
 from .batch import reconstruct_batch  # noqa: F401
+from .kld_net import Unet, detect_motion_lines, get_unet, kld_net_input, movement_masks_from_kspace  # noqa: F401
 from .metrics import calmetric2D, crop_metrics, my_psnr, normalize, rmse  # noqa: F401
 from .motion_utils import (extract_movement_groups, generate_list, get_rand_int, lines_from_mask,  # noqa: F401
                            motion_simulation2D, rotation_matrix_2d)
@@ -27,5 +28,6 @@ __all__ = [
     "GradientEntropyLoss", "extract_movement_groups", "lines_from_mask", "FitEngine",
     "LineStructure", "lambda_schedule", "build", "lib", "reconstruct_batch", "reconstruct_slices",
     "gather_images", "shard_indices", "calmetric2D", "crop_metrics", "my_psnr", "normalize", "rmse",
+    "get_unet", "Unet", "kld_net_input", "detect_motion_lines", "movement_masks_from_kspace",
     "motion_simulation2D", "generate_list", "get_rand_int", "rotation_matrix_2d",
 ]

@@ -111,3 +111,76 @@ def test_crop_metrics_on_complex_reconstruction(h, w):
     assert abs(float(psnr) - want["psnr"]) < 1e-3
     assert abs(float(ssim) - want["ssim"]) < 2e-5
     assert abs(float(rmse) - want["rmse"]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# f1: kld-net (U-Net) inference -> movement groups
+# ---------------------------------------------------------------------------------------------------
+from oracle import kld_net_oracle as ko  # noqa: E402
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_unet_matches_reference_golden(golden_dir, tag):
+    """Outputs of the reference's own src/models/unet.py (oracle/gen_golden_unet.py) on seeded weights."""
+    g = np.load(f"{golden_dir}/unet_small.npz")
+    in_c, out_c, chans, pools, n, h, w, seed = (int(v) for v in g[f"{tag}_cfg"])
+    net = mb.get_unet(in_c, out_c, chans, pools, 0.0)
+    net.load_state_dict(ko.init_unet_state(seed, in_c, out_c, chans, pools))
+    net = net.cuda()
+    y = net(torch.from_numpy(g[f"{tag}_x"]).to(DEV))
+    want = torch.from_numpy(g[f"{tag}_y"])
+    assert y.shape == want.shape
+    assert rel_l2(y, want) < 2e-5, rel_l2(y, want)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 320, 320), (1, 640, 368), (3, 64, 48)])
+def test_unet_full_size_matches_oracle(n, h, w):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    state = ko.init_unet_state(3)
+    net = mb.get_unet(2, 1, 32, 4, 0.0)
+    net.load_state_dict(state)
+    net = net.cuda()
+    x = torch.randn(n, 2, h, w, generator=torch.Generator().manual_seed(h)).to(DEV) * 2.0
+    y = net(x)
+    want = ko.unet_forward({k: v.to(DEV) for k, v in state.items()}, x)
+    print(f"unet {n}x{h}x{w}: rel-L2 vs torch fp32 {rel_l2(y, want):.2e}")
+    assert rel_l2(y, want) < 5e-5
+
+
+def test_kld_net_to_movement_groups_pipeline():
+    """test_immoco.py:47-61 end to end: k-space -> network input -> logits -> mask -> column vote ->
+    groups, against the oracle's restatement on the same seeded weights; then the fit accepts them."""
+    h = w = 64
+    case = orc.make_case(h, w, 2, 4)
+    k = case["kspace_motion"]
+    state = ko.init_unet_state(11, gain=3.0)
+    net = mb.get_unet(2, 1, 32, 4, 0.0)
+    net.load_state_dict(state)
+    net = net.cuda()
+    x_o = ko.kld_net_input(k, orc.IFFT)
+    x = mb.kld_net_input(k.to(DEV))
+    assert rel_l2(x, x_o) < 1e-5
+    logits_o = ko.unet_forward(state, x_o)
+    logits = net(x)
+    assert rel_l2(logits, logits_o) < 1e-4
+    lines_o = ko.motion_lines_from_logits(logits_o)
+    lines = mb.detect_motion_lines(net, k.to(DEV))
+    # pixels whose logit sits within rounding of 0 may flip; the 20 % column vote must not
+    assert lines.shape == (1, w) and torch.equal(lines[0].cpu(), lines_o)
+    masks = mb.movement_masks_from_kspace(net, k.to(DEV)[None])
+    want = orc.extract_movement_groups(lines_o, make_list=True, height=h)
+    assert torch.equal(masks[0].cpu(), want)
+    if masks[0].shape[0] > 0:
+        im, _ = mb.imcoco_motion_correction(k.to(DEV), masks[0], iters=10)
+        assert im.shape == (h, w) and bool(torch.isfinite(torch.view_as_real(im)).all())
+
+
+def test_unet_rejects_unsupported():
+    net = mb.get_unet(2, 1, 8, 4, 0.0).cuda()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 2, 40, 40, device=DEV))          # 40 is not a multiple of 16
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 32, 32, device=DEV))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 32, 32))

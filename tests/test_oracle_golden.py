@@ -106,3 +106,32 @@ def test_metrics_sane():
     a = torch.rand(64, 64)
     m = orc.crop_metrics(a, a)
     assert m["ssim"] > 0.999999 and m["rmse"] == 0.0
+
+
+def test_kld_net_oracle_against_reference_unet_golden(golden_dir):
+    """oracle/kld_net_oracle.py vs outputs of the reference's own src/models/unet.py
+    (oracle/gen_golden_unet.py checked bit-equality in the build container)."""
+    from oracle import kld_net_oracle as ko
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    for tag in ("a", "c"):
+        in_c, out_c, chans, pools, n, h, w, seed = (int(v) for v in g[f"{tag}_cfg"])
+        state = ko.init_unet_state(seed, in_c, out_c, chans, pools)
+        y = ko.unet_forward(state, torch.from_numpy(g[f"{tag}_x"]), pools)
+        want = torch.from_numpy(g[f"{tag}_y"])
+        assert y.shape == want.shape
+        assert float((y - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    spec = ko.unet_state_spec(2, 1, 32, 4)
+    assert len(spec) == 24 and sum(int(np.prod(s)) for _, s in spec) == 7756385
+
+
+def test_get_unet_has_fastmri_state_dict_layout():
+    """kLDNet.pth (fastmri.models.Unet(2,1,32,4)) must load into the CUDA-path module unchanged."""
+    import miccai24_immoco_b200 as mb
+    from oracle import kld_net_oracle as ko
+    net = mb.get_unet(in_chans=2, out_chans=1, chans=32, num_pool_layers=4, drop_prob=0.0)
+    spec = ko.unet_state_spec(2, 1, 32, 4)
+    sd = net.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s in spec)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 32, 32))          # CPU tensors: no fallback
