@@ -22,7 +22,7 @@ import torch
 
 from .immoco import FitEngine, IMMoCo, lambda_schedule
 
-DEFAULT_IN_FLIGHT = 3
+DEFAULT_IN_FLIGHT = 1
 DEFAULT_CHUNK = 10
 
 

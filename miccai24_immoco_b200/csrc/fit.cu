@@ -236,6 +236,7 @@ struct AuxStream {
   cudaEvent_t fork = nullptr, join_fwd = nullptr, mlp_done = nullptr, join_end = nullptr;
 };
 static std::mutex g_aux_mutex;
+static int g_aux_high_priority = 1;
 static AuxStream* aux_for(cudaStream_t owner) {
   static AuxStream table[256];
   static int used = 0;
@@ -248,7 +249,13 @@ static AuxStream* aux_for(cudaStream_t owner) {
   AuxStream a;
   a.dev = dev;
   a.owner = owner;
-  if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  // the image branch is short and the motion chain waits on it at the forward join: give it the
+  // higher scheduling priority so its CTAs are placed first whenever both streams have work queued
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, g_aux_high_priority ? prio_hi : prio_lo) !=
+      cudaSuccess)
+    return nullptr;
   cudaEvent_t* ev[4] = {&a.fork, &a.join_fwd, &a.mlp_done, &a.join_end};
   for (auto e : ev)
     if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
