@@ -180,6 +180,9 @@ int immoco_fit_run(const immoco_fit* fit, int32_t it_begin, int32_t it_end,
 /* 1 (default): the image-INR branch of every non-instrumented iteration runs on an internal
  * auxiliary stream, forked from / joined to `stream` with events; 0: everything on `stream`. */
 int immoco_set_branch_overlap(int32_t on);
+/* 1 (default): kernels are launched with programmatic dependent launch (griddepcontrol): a kernel's
+ * launch and prologue overlap its predecessor's tail; 0: plain stream order. Results are identical. */
+int immoco_set_pdl(int32_t on);
 
 /* ---- (9) evaluation metrics on the device: replaces calmetric2D's normalize / my_psnr / piq.ssim /
  *          rmse (src/utils/evaluate.py:19-47,57-80; caller src/test/test_immoco.py:74-85).

@@ -111,6 +111,7 @@ _SIGNATURES = {
     "immoco_profile_timeline": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "immoco_set_profile_overlap": (C.c_int, [C.c_int32]),
     "immoco_set_branch_overlap": (C.c_int, [C.c_int32]),
+    "immoco_set_pdl": (C.c_int, [C.c_int32]),
     "immoco_abi_version": (C.c_int, []),
     "immoco_launches_per_iteration": (C.c_int, [C.c_int32]),
     "immoco_struct_sizes": (None, [C.POINTER(C.c_int32)]),

@@ -13,6 +13,35 @@
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins
+// with pdl_wait() (griddepcontrol.wait: the preceding kernel of the stream has completed and its
+// writes are visible), so the ~18 dependent launches of an iteration are resolved on the device
+// instead of by the host-side stream scheduler: 826 -> 808 us per iteration on B200
+// (profiles/round1_v5_pdl_ab.txt).  No kernel triggers its dependents early
+// (griddepcontrol.launch_dependents at CTA start was measured SLOWER, 966 us: the early-resident CTAs
+// of the next kernel take SM resources from the last wave of the running one).
+// Work done BEFORE pdl_wait() may only read buffers written at least two kernels earlier (MLP weights).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+int immoco_pdl_enabled();   // fit.cu
+
+template <typename... P, typename... A>
+inline cudaError_t immoco_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = immoco_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------

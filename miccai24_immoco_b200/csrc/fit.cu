@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
             float4* __restrict__ v, int64_t n4, float one_minus_b1, float b2, float one_minus_b2,
             float step_size, float bc2_sqrt, float eps, int zero_grad) {
+  pdl_wait();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
     float4 ga[U], ma[U], va[U], pa[U];
@@ -70,6 +71,7 @@ adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__
 __global__ void adam_tail_kernel(float* p, float* g, float* m, float* v, int64_t begin, int64_t n,
                                  float one_minus_b1, float b2, float one_minus_b2, float step_size,
                                  float bc2_sqrt, float eps, int zero_grad) {
+  pdl_wait();
   const int64_t i = begin + threadIdx.x;
   if (i < n) {
     const float gi = g[i];
@@ -82,6 +84,11 @@ __global__ void adam_tail_kernel(float* p, float* g, float* m, float* v, int64_t
 }
 
 }  // namespace
+
+static int g_pdl = 1;
+int immoco_pdl_enabled() { return g_pdl; }
+// 1 (default): hot-path kernels are launched with programmatic stream serialization (common.cuh)
+extern "C" int immoco_set_pdl(int32_t on) { g_pdl = on ? 1 : 0; return 0; }
 
 static int g_adam_variant = 0, g_adam_ctas_per_sm = 32;
 // tuning knobs (tools/adam_bench.py): variant = {U=1,2,4} x {plain, streaming hints}; CTAs per SM
@@ -113,7 +120,7 @@ extern "C" int immoco_adam_step(float* params, float* grads, float* exp_avg, flo
     const int64_t cap = (int64_t)IMMOCO_NUM_SMS * g_adam_ctas_per_sm;
     if (blocks > cap) blocks = cap;
 #define IMMOCO_ADAM_LAUNCH(U, H)                                                                          \
-  adam_kernel<U, H><<<(unsigned)blocks, 256, 0, s>>>((float4*)params, (float4*)grads, (float4*)exp_avg,   \
+  immoco_launch(adam_kernel<U, H>, dim3((unsigned)blocks), dim3(256), 0, s, (float4*)params, (float4*)grads, (float4*)exp_avg,   \
                                                      (float4*)exp_avg_sq, n4, omb1, (float)beta2, omb2,   \
                                                      step_size, bc2_sqrt, (float)eps, zero_grad)
     switch (g_adam_variant) {
@@ -128,7 +135,7 @@ extern "C" int immoco_adam_step(float* params, float* grads, float* exp_avg, flo
     IMMOCO_LAUNCH_CHECK();
   }
   if (n4 * 4 < n) {
-    adam_tail_kernel<<<1, 4, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n4 * 4, n, omb1, (float)beta2, omb2,
+    immoco_launch(adam_tail_kernel, dim3(1), dim3(4), 0, s, params, grads, exp_avg, exp_avg_sq, n4 * 4, n, omb1, (float)beta2, omb2,
                                      step_size, bc2_sqrt, (float)eps, zero_grad);
     IMMOCO_LAUNCH_CHECK();
   }

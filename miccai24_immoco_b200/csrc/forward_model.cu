@@ -31,6 +31,7 @@ fft_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int row
                 const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
                 const float* __restrict__ in_w, const float* __restrict__ out_w, float scale,
                 int accumulate) {
+  pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* a = tw + W;
@@ -81,6 +82,7 @@ template <bool INV>
 __global__ void __launch_bounds__(kThreads)
 fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, int H, int W,
                 const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g, float scale) {
+  pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   const int HP = H + 1;
   float2* tw = sm2;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(kThreads)
 colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ k_in,
                     float2* __restrict__ k_out, float2* __restrict__ d_c, double* __restrict__ loss_acc,
                     int H, int W, const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g) {
+  pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   __shared__ float red[kThreads / 32];
   const int HP = H + 1;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(kThreads)
 motion_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ disp,
                        const float2* __restrict__ ident, const __grid_constant__ immoco_lines lines,
                        const float2* __restrict__ tw_g, float2* __restrict__ c_out, int H, int W) {
+  pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* row = tw + W;
@@ -244,6 +248,7 @@ motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict_
                        const __grid_constant__ immoco_lines lines, const float2* __restrict__ tw_g,
                        float2* __restrict__ d_image, float2* __restrict__ d_disp, int pre_tanh, int H,
                        int W) {
+  pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* gl = tw + W;
@@ -331,6 +336,7 @@ __device__ __forceinline__ float ge_dloss_dg(float g) {
 __global__ void __launch_bounds__(kThreads)
 grad_entropy_kernel(const float2* __restrict__ img, float grad_scale, double* __restrict__ loss_acc,
                     float2* __restrict__ d_img, int accumulate, int H, int W) {
+  pdl_wait();
   __shared__ float red[kThreads / 32];
   const int P = H * W;
   float part = 0.0f;
@@ -410,11 +416,11 @@ int launch_rows(const float* in, float* out, int rows, int W, const FftPlan& pla
   const int grid = (rows + kRowsPerCta - 1) / kRowsPerCta;
   if (inv) {
     allow_smem(fft_rows_kernel<true>, smem);
-    fft_rows_kernel<true><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, rows, W, plan,
+    immoco_launch(fft_rows_kernel<true>, dim3(grid), dim3(kThreads), smem, s, (const float2*)in, (float2*)out, rows, W, plan,
                                                       (const float2*)tw, in_w, out_w, scale, accumulate);
   } else {
     allow_smem(fft_rows_kernel<false>, smem);
-    fft_rows_kernel<false><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, rows, W, plan,
+    immoco_launch(fft_rows_kernel<false>, dim3(grid), dim3(kThreads), smem, s, (const float2*)in, (float2*)out, rows, W, plan,
                                                        (const float2*)tw, in_w, out_w, scale, accumulate);
   }
   IMMOCO_LAUNCH_CHECK();
@@ -430,11 +436,11 @@ int launch_cols(const float* in, float* out, int batch, int H, int W, const FftP
   dim3 grid((W + kColsPerCta - 1) / kColsPerCta, batch);
   if (inv) {
     allow_smem(fft_cols_kernel<true>, smem);
-    fft_cols_kernel<true><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, H, W, plan,
+    immoco_launch(fft_cols_kernel<true>, dim3(grid), dim3(kThreads), smem, s, (const float2*)in, (float2*)out, H, W, plan,
                                                       (const float2*)tw, scale);
   } else {
     allow_smem(fft_cols_kernel<false>, smem);
-    fft_cols_kernel<false><<<grid, kThreads, smem, s>>>((const float2*)in, (float2*)out, H, W, plan,
+    immoco_launch(fft_cols_kernel<false>, dim3(grid), dim3(kThreads), smem, s, (const float2*)in, (float2*)out, H, W, plan,
                                                        (const float2*)tw, scale);
   }
   IMMOCO_LAUNCH_CHECK();
@@ -448,7 +454,7 @@ int launch_motion_fwd(const float* image, const float* disp, const float* ident,
   const size_t smem = (size_t)2 * W * sizeof(float2);
   allow_smem(motion_rows_fwd_kernel, smem);
   dim3 grid(H, lines->n_groups);
-  motion_rows_fwd_kernel<<<grid, kThreads, smem, s>>>((const float2*)image, (const float2*)disp,
+  immoco_launch(motion_rows_fwd_kernel, dim3(grid), dim3(kThreads), smem, s, (const float2*)image, (const float2*)disp,
                                                      (const float2*)ident, *lines, (const float2*)tw_w,
                                                      (float2*)c_out, H, W);
   IMMOCO_LAUNCH_CHECK();
@@ -463,7 +469,7 @@ int launch_motion_bwd(const float* d_c, const float* image, const float* disp, c
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
   allow_smem(motion_rows_bwd_kernel, smem);
   dim3 grid(H, lines->n_groups);
-  motion_rows_bwd_kernel<<<grid, kThreads, smem, s>>>((const float2*)d_c, (const float2*)image,
+  immoco_launch(motion_rows_bwd_kernel, dim3(grid), dim3(kThreads), smem, s, (const float2*)d_c, (const float2*)image,
                                                      (const float2*)disp, (const float2*)ident, *lines,
                                                      (const float2*)tw_w, (float2*)d_image,
                                                      (float2*)d_disp, pre_tanh, H, W);
@@ -520,7 +526,7 @@ extern "C" int immoco_colpass_loss(const float* c, const float* k_in, float* k_o
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
   allow_smem(colpass_loss_kernel, smem);
   const int grid = (w + kColsPerCta - 1) / kColsPerCta;
-  colpass_loss_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+  immoco_launch(colpass_loss_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, 
       (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
       (const float2*)tw_h);
   IMMOCO_LAUNCH_CHECK();
@@ -533,7 +539,7 @@ extern "C" int immoco_grad_entropy(const float* image, float grad_scale, double*
   if (h < 1 || w < 1) return IMMOCO_ERR_BAD_ARG;
   const int P = h * w;
   int grid = (P + kThreads - 1) / kThreads;
-  grad_entropy_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float2*)image, grad_scale,
+  immoco_launch(grad_entropy_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const float2*)image, grad_scale,
                                                                   loss_acc, (float2*)d_image,
                                                                   accumulate, h, w);
   IMMOCO_LAUNCH_CHECK();

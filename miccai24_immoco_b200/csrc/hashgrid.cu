@@ -16,6 +16,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads)
 hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
                     const float2* __restrict__ table, float2* __restrict__ enc, int n, int level0) {
+  pdl_wait();
   const int level = level0 + blockIdx.y;
   const float scale = g.scale[level];
   const uint32_t res = g.resolution[level];
@@ -58,6 +59,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads)
 hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
                     const float2* __restrict__ d_enc, float2* __restrict__ grad_table, int n, int level0) {
+  pdl_wait();
   const int level = level0 + blockIdx.y;
   const float scale = g.scale[level];
   const uint32_t res = g.resolution[level];
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kThreads)
 hashgrid_fwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
                          const float2* __restrict__ table, float2* __restrict__ enc, int n, int level0,
                          int n_levels, int tiles) {
+  pdl_wait();
   // CTAs walk (level, tile) items in level-major order: one level's table (<= 4 MB) is the L2 working
   // set at any time; with a capped grid (immoco_set_hashgrid_ctas_per_sm) the CTAs are persistent
   for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
@@ -261,6 +264,7 @@ __global__ void __launch_bounds__(kThreads)
 hashgrid_bwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
                          const float2* __restrict__ d_enc, float2* __restrict__ grad_table, int n, int level0,
                          int n_levels, int tiles) {
+  pdl_wait();
   for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
     const int level = level0 + item / tiles;
     const int base = (item % tiles) * kPairPoints;
@@ -305,15 +309,15 @@ static int run_fwd(const immoco_grid_desc* grid, const float* coords, const floa
     const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
     const unsigned g = (unsigned)(items < cap ? items : cap);
     if (grid->n_dims == 2)
-      hashgrid_fwd_pair_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0, l1 - l0, tiles);
+      immoco_launch(hashgrid_fwd_pair_kernel<2>, dim3(g), dim3(kThreads), 0, s, *grid, coords, (const float2*)table, (float2*)enc, n, l0, l1 - l0, tiles);
     else
-      hashgrid_fwd_pair_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0, l1 - l0, tiles);
+      immoco_launch(hashgrid_fwd_pair_kernel<3>, dim3(g), dim3(kThreads), 0, s, *grid, coords, (const float2*)table, (float2*)enc, n, l0, l1 - l0, tiles);
   } else {
     dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(l1 - l0));
     if (grid->n_dims == 2)
-      hashgrid_fwd_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0);
+      immoco_launch(hashgrid_fwd_kernel<2>, dim3(g), dim3(kThreads), 0, s, *grid, coords, (const float2*)table, (float2*)enc, n, l0);
     else
-      hashgrid_fwd_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)table, (float2*)enc, n, l0);
+      immoco_launch(hashgrid_fwd_kernel<3>, dim3(g), dim3(kThreads), 0, s, *grid, coords, (const float2*)table, (float2*)enc, n, l0);
   }
   IMMOCO_LAUNCH_CHECK();
   return 0;
@@ -338,14 +342,14 @@ static int run_bwd(const immoco_grid_desc* grid, const float* coords, const floa
       const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
       const unsigned gp = (unsigned)(items < cap ? items : cap);
       if (grid->n_dims == 2)
-        hashgrid_bwd_pair_kernel<2><<<gp, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);
+        immoco_launch(hashgrid_bwd_pair_kernel<2>, dim3(gp), dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);
       else
-        hashgrid_bwd_pair_kernel<3><<<gp, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);
+        immoco_launch(hashgrid_bwd_pair_kernel<3>, dim3(gp), dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);
     } else {
       if (grid->n_dims == 2)
-        hashgrid_bwd_kernel<2><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a);
+        immoco_launch(hashgrid_bwd_kernel<2>, dim3(g), dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a);
       else
-        hashgrid_bwd_kernel<3><<<g, kThreads, 0, s>>>(*grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a);
+        immoco_launch(hashgrid_bwd_kernel<3>, dim3(g), dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a);
     }
     IMMOCO_LAUNCH_CHECK();
     a = b;
