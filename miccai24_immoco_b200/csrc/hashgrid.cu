@@ -241,20 +241,40 @@ __device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, 
                                               uint32_t res, uint32_t entries) {
   const int half = threadIdx.x & 1;
   const int i = base + (threadIdx.x >> 1);
-  if (i >= n) return;
-  const float2 go = __ldg(d_enc_level + i);
-  if (go.x == 0.0f && go.y == 0.0f) return;              // adding +-0 is a no-op
+  float2 go = make_float2(0.f, 0.f);
   uint32_t cell[D];
   float frac[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+  for (int d = 0; d < D; ++d) { cell[d] = 0; frac[d] = 0.f; }
+  if (i < n) {
+    go = __ldg(d_enc_level + i);
+#pragma unroll
+    for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+  }
+  const bool live = !(go.x == 0.0f && go.y == 0.0f);      // adding +-0 is a no-op (also covers i >= n)
   PairTerms<D, MODE> pt;
   pt.init(cell, half, entries, res, 1u);
   const float w0 = half ? frac[0] : 1.0f - frac[0];
+  // Even base cell (hash prime 1 on dimension 0): the two lanes' rows are idx and idx ^ 1, one aligned
+  // 16-byte slot -> ONE 128-bit reduction (RED.ADD.F32x4) issued by the even lane instead of two 64-bit
+  // ones.  Both lanes of a pair hold the same point, so the predicate is pair-uniform.
+  const bool merge = (MODE == kIdxHash) && ((cell[0] & 1u) == 0u);
 #pragma unroll
   for (int c = 0; c < (1 << (D - 1)); ++c) {
     const float w = pair_weight<D>(frac, w0, c);
-    atomicAdd(gtab + pt.index(c), make_float2(w * go.x, w * go.y));
+    const uint32_t idx = pt.index(c);
+    const float vx = w * go.x, vy = w * go.y;
+    const float ox = __shfl_xor_sync(0xffffffffu, vx, 1);
+    const float oy = __shfl_xor_sync(0xffffffffu, vy, 1);
+    if (!live) continue;
+    if (merge) {
+      if (half == 0) {
+        const float4 v = (idx & 1u) ? make_float4(ox, oy, vx, vy) : make_float4(vx, vy, ox, oy);
+        atomicAdd(reinterpret_cast<float4*>(gtab + (idx & ~1u)), v);
+      }
+    } else {
+      atomicAdd(gtab + idx, make_float2(vx, vy));
+    }
   }
 }
 
