@@ -224,6 +224,15 @@ int immoco_unet_instnorm_lrelu(float* x, const double* stats, float* pooled, int
 int immoco_unet_conv1x1(const float* in, const float* weight, const float* bias, float* out, int32_t n,
                         int32_t cin, int32_t cout, int32_t hw, void* stream);
 
+/* ---- (12) autofocusing baseline (src/models/autofocusing.py:69-84): n_mov complex images, each warped
+ *          by its own affine theta (n_mov, 6) as F.grid_sample(F.affine_grid(theta, align_corners=True),
+ *          mode="bicubic", zeros padding, align_corners=False); the backward pass reduces the output
+ *          cotangent straight to d theta (n_mov*6 doubles, ZEROED by the caller). ----------------------- */
+int immoco_rigid_bicubic_fwd(const float* images, const float* theta, float* out, int32_t n_mov, int32_t h,
+                             int32_t w, void* stream);
+int immoco_rigid_bicubic_bwd_theta(const float* images, const float* theta, const float* d_out, double* d_theta,
+                                   int32_t n_mov, int32_t h, int32_t w, void* stream);
+
 /* library/ABI version and the number of kernel launches one fit iteration issues */
 int immoco_abi_version(void);
 /* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit): lets a foreign-language

@@ -14,6 +14,7 @@ from ._native import build, lib, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
 from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_config,  # noqa: F401
                      imcoco_motion_correction, lambda_schedule, make_grids, mot_network_config,
                      network_config)
+from .autofocusing import Autofocusing, autofocus_motion_correction  # noqa: F401
 from .batch import reconstruct_batch  # noqa: F401
 from .kld_net import Unet, detect_motion_lines, get_unet, kld_net_input, movement_masks_from_kspace  # noqa: F401
 from .metrics import calmetric2D, crop_metrics, my_psnr, normalize, rmse  # noqa: F401
@@ -28,6 +29,6 @@ __all__ = [
     "GradientEntropyLoss", "extract_movement_groups", "lines_from_mask", "FitEngine",
     "LineStructure", "lambda_schedule", "build", "lib", "reconstruct_batch", "reconstruct_slices",
     "gather_images", "shard_indices", "calmetric2D", "crop_metrics", "my_psnr", "normalize", "rmse",
-    "get_unet", "Unet", "kld_net_input", "detect_motion_lines", "movement_masks_from_kspace",
+    "Autofocusing", "autofocus_motion_correction", "get_unet", "Unet", "kld_net_input", "detect_motion_lines", "movement_masks_from_kspace",
     "motion_simulation2D", "generate_list", "get_rand_int", "rotation_matrix_2d",
 ]

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libimmoco_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu", "unet.cu"]
+SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu", "unet.cu", "autofocus.cu"]
 
 MAX_LEVELS = 16
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -105,6 +105,8 @@ _SIGNATURES = {
     "immoco_unet_convt2x2": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_unet_instnorm_lrelu": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
     "immoco_unet_conv1x1": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "immoco_rigid_bicubic_fwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "immoco_rigid_bicubic_bwd_theta": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_profile_create": (_P, [C.c_int32]),
     "immoco_profile_destroy": (None, [_P]),
     "immoco_profile_read": (C.c_int, [_P, C.POINTER(C.c_float)]),

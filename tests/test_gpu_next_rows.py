@@ -184,3 +184,68 @@ def test_unet_rejects_unsupported():
         net(torch.zeros(1, 3, 32, 32, device=DEV))
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 2, 32, 32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# f3: autofocusing baseline on the same kernels
+# ---------------------------------------------------------------------------------------------------
+from oracle import autofocus_oracle as ao  # noqa: E402
+
+
+def _af_case(golden, tag):
+    h, w, n_mov, seed, iters = (int(v) for v in golden[f"{tag}_cfg"])
+    case = orc.make_case(h, w, n_mov, seed)
+    return case, h, w, iters
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_autofocusing_forward_matches_reference_golden(golden_dir, tag):
+    g = np.load(f"{golden_dir}/autofocus_small.npz")
+    case, h, w, _ = _af_case(g, tag)
+    k = case["kspace_motion"]
+    k = (k / orc.IFFT(k).abs().max()).to(DEV)
+    model = mb.Autofocusing(case["masks"].to(DEV))
+    p0 = torch.from_numpy(g[f"{tag}_p0"]).to(DEV)
+    with torch.no_grad():
+        for name, v in zip(("rot_vector", "x_shifts", "y_shifts"), p0):
+            model.motion_parameters[name].copy_(v)
+    got = model(k)
+    assert rel_l2(got, torch.from_numpy(g[f"{tag}_k_fwd"])) < 2e-5
+
+
+@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 40, 3)])
+def test_autofocusing_gradients_match_oracle(h, w, n_mov):
+    case = orc.make_case(h, w, n_mov, 8)
+    k = case["kspace_motion"]
+    k = k / orc.IFFT(k).abs().max()
+    masks = case["masks"]
+    g = torch.Generator().manual_seed(2)
+    p0 = [((torch.rand(n_mov, generator=g) - 0.5) * s) for s in (6.0, 5.0, 5.0)]
+    po = [p.clone().requires_grad_(True) for p in p0]
+    loss_o = orc.gradient_entropy(orc.IFFT(ao.autofocus_forward(k, masks, *po))) * 1e-4
+    loss_o.backward()
+    model = mb.Autofocusing(masks.to(DEV))
+    with torch.no_grad():
+        for name, v in zip(("rot_vector", "x_shifts", "y_shifts"), p0):
+            model.motion_parameters[name].copy_(v.to(DEV))
+    loss = mb.GradientEntropyLoss()(mb.IFFT(model(k.to(DEV)))) * 1e-4
+    loss.backward()
+    assert abs(float(loss) - float(loss_o)) < 1e-5 * abs(float(loss_o))
+    for name, ref in zip(("rot_vector", "x_shifts", "y_shifts"), po):
+        got = model.motion_parameters[name].grad
+        assert rel_l2(got, ref.grad) < 2e-3, (name, got, ref.grad)
+
+
+def test_autofocusing_loop_follows_reference_trajectory(golden_dir):
+    """Adam(lr=1) is sign-like in the first steps, so the parameter trajectory is checked to the
+    reference's golden one with a tolerance that allows rounding-level gradient differences."""
+    g = np.load(f"{golden_dir}/autofocus_small.npz")
+    case, h, w, iters = _af_case(g, "a")
+    img, k_ref, trace = mb.autofocus_motion_correction(case["kspace_motion"], case["masks"], iters=iters,
+                                                       return_trace=True)
+    assert img.shape == (h, w) and k_ref.dtype == torch.complex64
+    want = g["a_trace"]
+    assert np.allclose(trace[:2], want[:2], rtol=1e-4)
+    assert np.allclose(trace, want, rtol=2e-2)
+    with pytest.raises(RuntimeError):
+        mb.Autofocusing(case["masks"])                     # CPU masks: no fallback

@@ -135,3 +135,21 @@ def test_get_unet_has_fastmri_state_dict_layout():
     assert all(tuple(sd[k].shape) == tuple(s) for k, s in spec)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 2, 32, 32))          # CPU tensors: no fallback
+
+
+def test_autofocus_oracle_against_reference_golden(golden_dir):
+    """oracle/autofocus_oracle.py vs the reference's own src/models/autofocusing.py outputs
+    (oracle/gen_golden_autofocus.py checked bit-equality in the build container)."""
+    from oracle import autofocus_oracle as ao
+    g = np.load(os.path.join(golden_dir, "autofocus_small.npz"))
+    h, w, n_mov, seed, iters = (int(v) for v in g["a_cfg"])
+    case = orc.make_case(h, w, n_mov, seed)
+    k = case["kspace_motion"]
+    k = k / orc.IFFT(k).abs().max()
+    p0 = [torch.from_numpy(v) for v in g["a_p0"]]
+    got = ao.autofocus_forward(k, case["masks"], *p0)
+    want = torch.from_numpy(g["a_k_fwd"])
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    _, _, trace, params = ao.autofocus_loop(case["kspace_motion"], case["masks"], iters)
+    assert np.allclose(trace, g["a_trace"], rtol=1e-4)
+    assert np.allclose(torch.stack(params).numpy(), g["a_params"], atol=1e-3)
