@@ -1,13 +1,17 @@
-"""Several slices in flight on one GPU ("within a GPU, batch B instances").
+"""A stack of slices on one GPU ("within a GPU, batch B instances").
 
 The reference reconstructs a stack slice by slice (src/test/test_immoco.py:45-72): every slice is an
-independent optimisation.  One 320x320 slice cannot keep a B200 busy -- its kernels alternate between
-L2-bound (hash-grid gathers / reductions), SM-bound (MLPs), HBM-bound (Adam) and latency-bound (FFT
-chain) phases -- so ``reconstruct_batch`` keeps ``in_flight`` slices going at once, each on its own
-CUDA stream (plus the library's per-stream auxiliary stream), and feeds them round-robin in chunks of
-iterations from ONE host thread.  Nothing on this path synchronises the host: inputs are uploaded
-stream-ordered from pinned memory, every slice's result is cloned on its stream, and the caller's
-stream waits on the slot streams at the end.
+independent optimisation.  ``reconstruct_batch`` runs that loop with nothing synchronising the host:
+inputs are uploaded stream-ordered from pinned memory, the k-space scale stays on the device, every
+slice's result is cloned on its stream, and the caller's stream waits on the slot streams at the end.
+``in_flight`` slices can be kept going at once, each on its own CUDA stream (plus the library's
+per-stream auxiliary stream), fed round-robin in chunks of iterations from ONE host thread.
+
+Measured on B200 (profiles/round1_v4_slices_in_flight.txt): more than one slice in flight does NOT
+raise throughput -- 854 us per slice-iteration with one, 916 / 925 with two / three -- because every
+large kernel of an iteration already fills the GPU (hash-grid: all thread slots, L2-bound; MLP backward:
+the whole register file; Adam: HBM through the same L2).  The default is therefore one slice at a time;
+the knob stays for smaller shapes.
 
 Per-slice results are what ``imcoco_motion_correction`` returns for the same inputs (same kernels,
 same schedule; only the order of floating-point atomics differs, as between any two runs).
