@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=1000, help="optimisation iterations per slice (metric: 1000)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-iters", type=int, default=5)
+    ap.add_argument("--cpu-iters", type=int, default=15)
     ap.add_argument("--ref-iters", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
