@@ -122,6 +122,18 @@ def algorithmic_bytes(slot: str, p: int, m: int, n_par: int, t_img: int, t_mot: 
     return table[slot]
 
 
+# what actually paces each kernel (ncu --set full, profiles/round1_v5_ncu_full.txt)
+LIMITERS = {
+    "hashgrid_bwd_motion": "L2 atomic throughput (ncu lts 82 %, DRAM 9.5 %): 52.4 M 8-byte reductions on hashed rows "
+                           "with no locality across pixels; DRAM traffic equals the algorithmic bytes",
+    "hashgrid_fwd_motion": "L2 / L1TEX gather rate (ncu l1tex 79 %, lts 62 %, DRAM 9 %): 52.4 M 8-byte gathers on hashed rows",
+    "hashgrid_bwd_image": "L2 atomic throughput (ncu lts 51 %)", "hashgrid_fwd_image": "L2 / L1TEX gather rate",
+    "adam_motion": "HBM (ncu DRAM 69 % of its peak; 5.2 TB/s algorithmic)", "adam_image": "HBM",
+    "mlp_bwd_motion": "tcgen05 issue + SIMT epilogue (ncu sm 44 %, tensor pipe 20 %)",
+    "mlp_bwd_image": "tcgen05 issue + SIMT epilogue (ncu sm 33 %, tensor pipe 23 %)",
+    "mlp_fwd_motion": "SIMT epilogue (tanhf)", "mlp_fwd_image": "latency (2.7 tiles per CTA)",
+}
+
 # SURVEY 8(d) / oracle.touched_entries(): distinct table rows touched at 320x320
 T_IMG_320 = 3041608
 T_MOT_320 = {2: 5917982, 4: 6513775, 8: 6756779}
@@ -266,6 +278,7 @@ def run_ours(args):
         "per_kernel_gbs": {k: round(algorithmic_bytes(k, p, N_MOV, n_par2, T_IMG_320, T_MOT_320[N_MOV]) / (v * 1e-3) / 1e9, 1)
                            for k, v in per_slot.items() if v > 0},
         "instrumented_iterations": n_prof,
+        "limiter": LIMITERS.get(dom, ""),
         "iteration": {"algorithmic_bytes": b_iter, "achieved": round(b_iter / (ms_per_iter * 1e-3) / 1e9, 1),
                       "frac": round(b_iter / (ms_per_iter * 1e-3) / 1e9 / peak, 4)},
     }

@@ -249,3 +249,25 @@ def test_autofocusing_loop_follows_reference_trajectory(golden_dir):
     assert np.allclose(trace, want, rtol=2e-2)
     with pytest.raises(RuntimeError):
         mb.Autofocusing(case["masks"])                     # CPU masks: no fallback
+
+
+# ---------------------------------------------------------------------------------------------------
+# the whole of src/test/test_immoco.py on synthetic data: simulate -> detect lines -> groups -> fit -> metrics
+# ---------------------------------------------------------------------------------------------------
+def test_pipeline_simulate_groups_fit_metrics():
+    """Every stage on the CUDA path (no oracle in the loop except the phantom): the corrected image must be
+    closer to the ground truth than the motion-corrupted one, like the reference's evaluation reports."""
+    h = w = 320                                   # the C2 golden case: seed 1004, n_M = 4 (29.6 dB corrupted)
+    gt = orc.make_phantom(h, w, 1004).to(DEV)
+    torch.manual_seed(1004)
+    k_motion, mask, rot, trans = mb.motion_simulation2D(gt, 4)
+    # movement groups from the (ground-truth) line mask through the reference's column vote (test_immoco.py:59-61)
+    masks = mb.extract_movement_groups(mb.lines_from_mask(mask), make_list=True, height=h)
+    assert masks.shape == (4, h, w)
+    corrupted = mb.IFFT(k_motion)
+    refined = mb.reconstruct_batch([k_motion], [masks], 200, 1e-2, 1e-2)[0]
+    psnr0, ssim0, _, rmse0 = mb.crop_metrics(corrupted, gt.abs())
+    psnr1, ssim1, _, rmse1 = mb.crop_metrics(refined, gt.abs())
+    print(f"corrupted: {float(psnr0):.2f} dB / {float(ssim0):.4f};  IM-MoCo 200 its: {float(psnr1):.2f} dB / {float(ssim1):.4f}")
+    assert float(psnr1) > float(psnr0) + 3.0 and float(ssim1) > float(ssim0)
+    assert float(rmse1) < float(rmse0)
