@@ -216,3 +216,34 @@ def test_adam_step_matches_torch(native_lib):
     nat.check(native_lib.immoco_adam_step(p1.data_ptr(), z.data_ptr(), zm.data_ptr(), zv.data_ptr(),
                                           1024, 1e-2, 0.9, 0.999, 1e-8, 1, 1, _s()), "adam")
     assert torch.equal(p0, p1)
+
+
+@pytest.mark.parametrize("width,act,n", [(64, "tanh", 409600), (256, "relu", 102400), (64, "tanh", 12345)])
+def test_tensor_core_mlp_is_run_to_run_deterministic(native_lib, width, act, n):
+    """The tcgen05 kernels hand work between issuing threads, TMEM regions and shared-memory buffers through
+    mbarriers only; a missing dependency would show as run-to-run differences.  d_enc and the forward output
+    involve no atomics, so they must be BIT-identical over many launches (the weight gradients are summed
+    across CTAs with atomics and may differ in the last bits)."""
+    native_lib.immoco_set_mlp_impl(1)
+    a = {"relu": nat.ACT_RELU, "tanh": nat.ACT_TANH}[act]
+    g = torch.Generator(device=DEV).manual_seed(n)
+    enc = torch.randn(16, n, 2, device=DEV, generator=g) * 3e-2
+    w1 = torch.randn(width, 32, device=DEV, generator=g) * 0.3
+    w2 = torch.randn(16, width, device=DEV, generator=g) * 0.3
+    d_out = torch.randn(n, 2, device=DEV, generator=g)
+    outs, d_encs, g1s = [], [], []
+    for _ in range(25):
+        out = torch.empty(n, 2, device=DEV)
+        d_enc = torch.empty_like(enc)
+        g1, g2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        nat.check(native_lib.immoco_mlp_fwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), n, width, a, 1,
+                                            _s()), "fwd")
+        nat.check(native_lib.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(),
+                                            d_enc.data_ptr(), g1.data_ptr(), g2.data_ptr(), n, width, a, _s()), "bwd")
+        outs.append(out)
+        d_encs.append(d_enc)
+        g1s.append(g1)
+    for k in range(1, 25):
+        assert torch.equal(outs[k], outs[0]), f"forward output differs in launch {k}"
+        assert torch.equal(d_encs[k], d_encs[0]), f"d_enc differs in launch {k}"
+        assert rel_l2(g1s[k], g1s[0]) < 1e-5
