@@ -76,6 +76,10 @@ int immoco_set_hashgrid_impl(int32_t pair);
 /* > 0: run the lane-pair kernels as persistent grids of this many 256-thread CTAs per SM (caps their
  * SM share when co-running); 0 (default): one CTA per (level, 128-point tile), hardware-balanced. */
 int immoco_set_hashgrid_ctas_per_sm(int32_t ctas);
+/* Same cap for the BACKWARD scatter kernels only (> 0 overrides the knob above for them): the scatter is
+ * paced by the L2 atomic units, so a thin persistent grid loses little and leaves the SMs' thread slots
+ * and registers to an SM-bound kernel of the other INR branch. */
+int immoco_set_hashgrid_bwd_ctas_per_sm(int32_t ctas);
 
 /* ---- (2) INR MLP: replaces the network half of tcnn.NetworkWithInputEncoding
  *          (configs at src/models/immoco.py:11-25).  One hidden layer of `width` (64 or 256),
@@ -239,6 +243,10 @@ int immoco_abi_version(void);
  * binding assert that its struct mirrors match this build. */
 void immoco_struct_sizes(int32_t out[3]);
 int immoco_launches_per_iteration(int32_t m);
+/* 1 (default): immoco_fit_run issues the static row pass and the pruned motion rows of an iteration as ONE
+ * launch forward and ONE launch for the adjoint (16 launches per iteration); 0: four separate launches
+ * (18 per iteration; A/B check -- results agree to rounding). */
+int immoco_set_fused_rows(int32_t on);
 
 #ifdef __cplusplus
 }

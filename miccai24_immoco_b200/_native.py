@@ -11,7 +11,8 @@ from typing import List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libimmoco_b200.so")
+# IMMOCO_LIB_PATH / IMMOCO_NVCC_FLAGS: build-variant experiments (tools/), not used by the product path
+LIB_PATH = os.environ.get("IMMOCO_LIB_PATH") or os.path.join(_HERE, "libimmoco_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu", "unet.cu", "autofocus.cu"]
 
@@ -82,6 +83,7 @@ _SIGNATURES = {
     "immoco_set_mlp_impl": (C.c_int, [C.c_int32]),
     "immoco_set_hashgrid_impl": (C.c_int, [C.c_int32]),
     "immoco_set_hashgrid_ctas_per_sm": (C.c_int, [C.c_int32]),
+    "immoco_set_hashgrid_bwd_ctas_per_sm": (C.c_int, [C.c_int32]),
     "immoco_set_adam_tuning": (C.c_int, [C.c_int32, C.c_int32]),
     "immoco_get_mlp_impl": (C.c_int, []),
     "immoco_fft2c": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32,
@@ -114,6 +116,7 @@ _SIGNATURES = {
     "immoco_set_profile_overlap": (C.c_int, [C.c_int32]),
     "immoco_set_branch_overlap": (C.c_int, [C.c_int32]),
     "immoco_set_pdl": (C.c_int, [C.c_int32]),
+    "immoco_set_fused_rows": (C.c_int, [C.c_int32]),
     "immoco_abi_version": (C.c_int, []),
     "immoco_launches_per_iteration": (C.c_int, [C.c_int32]),
     "immoco_struct_sizes": (None, [C.POINTER(C.c_int32)]),
@@ -127,7 +130,7 @@ def nvcc_command(out_path: str = LIB_PATH) -> List[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
             "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(_ROOT, "include"),
-            "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+            "-o", out_path] + os.environ.get("IMMOCO_NVCC_FLAGS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
 
 
 def needs_build() -> bool:

@@ -15,6 +15,13 @@ int immoco_motion_rows_fwd(const float* image, const float* disp, const float* i
 int immoco_motion_rows_bwd(const float* d_c, const float* image, const float* disp, const float* ident,
                            const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp,
                            int h, int w, void* stream);
+int immoco_rows_fwd_fused(const float* image, const float* disp, const float* ident, const immoco_lines* lines,
+                          const float* tw_w, float* c_out, int h, int w, void* stream);
+int immoco_rows_bwd_fused(const float* d_c, const float* image, const float* disp, const float* ident,
+                          const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp, int h, int w,
+                          void* stream);
+int immoco_colpass_loss_zero(float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
+                             const float* tw_h, int h, int w, void* stream);
 
 namespace {
 
@@ -150,9 +157,14 @@ extern "C" void immoco_struct_sizes(int32_t out[3]) {
   out[2] = (int32_t)sizeof(immoco_fit);
 }
 
-// hashgrid fwd + mlp fwd (x2), rows, motion rows, colpass, GE, rows adj, motion rows bwd,
+// hashgrid fwd + mlp fwd (x2), fused rows (static + motion groups), colpass, GE, fused adjoint rows,
 // mlp bwd + hashgrid bwd (dense levels + hashed levels: 2 launches) (x2), adam (x2: motion, image)
-extern "C" int immoco_launches_per_iteration(int32_t m) { return m > 0 ? 18 : 10; }
+static int g_fuse_rows = 1;
+extern "C" int immoco_launches_per_iteration(int32_t m) { return m > 0 ? (g_fuse_rows ? 16 : 18) : 10; }
+
+// 1 (default): the static row pass and the pruned motion rows of an iteration are ONE launch (forward) and
+// ONE launch (adjoint); 0: the four separate launches (A/B check)
+extern "C" int immoco_set_fused_rows(int32_t on) { g_fuse_rows = on ? 1 : 0; return 0; }
 
 #define IMMOCO_TRY(expr)          \
   do {                            \
@@ -306,6 +318,10 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
   AuxStream* aux = (g_overlap && M > 0) ? aux_for(ms) : nullptr;
   bool forked = false;          // aux currently carries work that `ms` has not joined
 
+  const bool fuse_rows = g_fuse_rows != 0;
+  // the fused row launch ADDS into c_tmp; the column pass re-zeroes it for the next iteration
+  if (fuse_rows && cudaMemsetAsync(f->c_tmp, 0, (size_t)P * 2 * sizeof(float), ms) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+
   for (int it = it_begin; it < it_end; ++it) {
     double* loss = f->loss + 2 * (int64_t)it;
     cudaEvent_t* ev = nullptr;
@@ -335,13 +351,22 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     K(2, ms, M > 0 ? immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream) : nop());
     K(3, ms, M > 0 ? immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream) : nop());
     if (two) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
-    K(4, ms, immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
-    K(5, ms, immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
-    K(6, ms, immoco_colpass_loss(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
-    // ---- backward ------------------------------------------------------------------------------
-    K(8, ms, immoco_rows_static(f->d_c, f->d_image, H, W, f->tw_w, f->lines.static_w, nullptr, 1, true, stream));
-    K(9, ms, M > 0 ? immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
-                                            f->d_image, f->d_disp, H, W, stream) : nop());
+    if (fuse_rows) {      // slots 4 / 8 (static row passes) are folded into slots 5 / 9
+      K(4, ms, nop());
+      K(5, ms, immoco_rows_fwd_fused(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
+      K(6, ms, immoco_colpass_loss_zero(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
+      K(8, ms, nop());
+      K(9, ms, immoco_rows_bwd_fused(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->d_image,
+                                     f->d_disp, H, W, stream));
+    } else {
+      K(4, ms, immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
+      K(5, ms, immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
+      K(6, ms, immoco_colpass_loss(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
+      // ---- backward ----------------------------------------------------------------------------
+      K(8, ms, immoco_rows_static(f->d_c, f->d_image, H, W, f->tw_w, f->lines.static_w, nullptr, 1, true, stream));
+      K(9, ms, M > 0 ? immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
+                                              f->d_image, f->d_disp, H, W, stream) : nop());
+    }
     K(10, ms, M > 0 ? immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
                                      gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream) : nop());
     if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }

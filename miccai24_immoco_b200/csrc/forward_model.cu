@@ -25,18 +25,18 @@ __device__ __forceinline__ int wrap_mod(int a, int n) {
 // Row pass: centred 1-D FFT along W of `rows` rows.
 //   out[r][l] (+)= scale * out_w[l] * sum_j in_w[j] * in[r][j] * exp(-/+ 2 pi i (l-W/2)(j-W/2)/W)
 // ------------------------------------------------------------------------------------------------
-template <bool INV>
-__global__ void __launch_bounds__(kThreads)
-fft_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int rows, int W,
-                const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
-                const float* __restrict__ in_w, const float* __restrict__ out_w, float scale,
-                int accumulate) {
-  pdl_wait();
+// ATOMIC: the result is ADDED with float atomics (entries whose output weight is zero are skipped) -- used
+// by the fused launches below, where CTAs of the pruned motion rows add into the same buffer concurrently.
+template <bool INV, bool ATOMIC>
+__device__ __forceinline__ void rows_body(const float2* __restrict__ in, float2* __restrict__ out, int rows, int W,
+                                          const FftPlan& plan, const float2* __restrict__ tw_g,
+                                          const float* __restrict__ in_w, const float* __restrict__ out_w,
+                                          float scale, int accumulate, int cta) {
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* a = tw + W;
   float2* b = a + kRowsPerCta * W;
-  const int r0 = blockIdx.x * kRowsPerCta;
+  const int r0 = cta * kRowsPerCta;
   const int nr = min(kRowsPerCta, rows - r0);
   const int half = W >> 1;
   for (int t = threadIdx.x; t < W; t += kThreads) tw[t] = __ldg(tw_g + t);
@@ -57,20 +57,35 @@ fft_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int row
     if (out_w) s *= __ldg(out_w + l);
     v.x *= s; v.y *= s;
     float2* o = out + (size_t)(r0 + r) * W + l;
-    if (accumulate) { const float2 p = *o; v.x += p.x; v.y += p.y; }
-    *o = v;
+    if (ATOMIC) {
+      if (s != 0.0f) atomicAdd(o, v);
+    } else {
+      if (accumulate) { const float2 p = *o; v.x += p.x; v.y += p.y; }
+      *o = v;
+    }
   }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(kThreads)
+fft_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int rows, int W,
+                const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
+                const float* __restrict__ in_w, const float* __restrict__ out_w, float scale,
+                int accumulate) {
+  pdl_wait();
+  rows_body<INV, false>(in, out, rows, W, plan, tw_g, in_w, out_w, scale, accumulate, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Column pass helpers: a CTA owns kColsPerCta adjacent columns of one (H,W) image.
 // smem transform t = column, stride HP = H+1 (bank spread), input/output rolled by H/2.
 // ------------------------------------------------------------------------------------------------
+template <int CPC = kColsPerCta>
 __device__ __forceinline__ void load_cols(float2* a, const float2* __restrict__ in, int H, int W,
                                           int l0, int nc, int HP) {
   const int half = H >> 1;
-  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
-    const int i = idx / kColsPerCta, c = idx - i * kColsPerCta;
+  for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads) {
+    const int i = idx / CPC, c = idx - i * CPC;
     if (c < nc) {
       int ii = i + half; if (ii >= H) ii -= H;
       a[c * HP + ii] = __ldg(in + (size_t)i * W + l0 + c);
@@ -111,29 +126,38 @@ fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, int H, 
 
 // Fused column pass of the fit loop:
 //   K = F_H(C);  loss += sum |K - K_in|^2;  dC = F_H^H((K - K_in) / (H W))
+// CPC adjacent columns per CTA: 4 (64-byte segments) when that still gives every SM a CTA, else 2
+template <int CPC>
 __global__ void __launch_bounds__(kThreads)
 colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ k_in,
                     float2* __restrict__ k_out, float2* __restrict__ d_c, double* __restrict__ loss_acc,
-                    int H, int W, const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g) {
+                    int H, int W, const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
+                    float2* __restrict__ zero_after_load) {
   pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   __shared__ float red[kThreads / 32];
   const int HP = H + 1;
   float2* tw = sm2;
   float2* a = tw + H;
-  float2* b = a + kColsPerCta * HP;
-  const int l0 = blockIdx.x * kColsPerCta;
-  const int nc = min(kColsPerCta, W - l0);
+  float2* b = a + CPC * HP;
+  const int l0 = blockIdx.x * CPC;
+  const int nc = min(CPC, W - l0);
   const int half = H >> 1;
   for (int t = threadIdx.x; t < H; t += kThreads) tw[t] = __ldg(tw_g + t);
-  load_cols(a, c_in, H, W, l0, nc, HP);
+  load_cols<CPC>(a, c_in, H, W, l0, nc, HP);
+  if (zero_after_load) {     // == c_in: the next iteration's fused row launch ADDS into a zeroed buffer
+    for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads) {
+      const int i = idx / CPC, c = idx - i * CPC;
+      if (c < nc) zero_after_load[(size_t)i * W + l0 + c] = make_float2(0.f, 0.f);
+    }
+  }
   __syncthreads();
   float2* res = fft_smem<false>(a, b, nc, HP, plan, tw);
   float2* other = (res == a) ? b : a;
   const float inv_hw = 1.0f / ((float)H * (float)W);
   float part = 0.0f;
-  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
-    const int k = idx / kColsPerCta, c = idx - k * kColsPerCta;
+  for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads) {
+    const int k = idx / CPC, c = idx - k * CPC;
     if (c < nc) {
       int kk = k + half; if (kk >= H) kk -= H;
       const float2 v = res[c * HP + kk];
@@ -156,8 +180,8 @@ colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ 
     atomicAdd(loss_acc, s);
   }
   const float2* adj = fft_smem<true>(res, other, nc, HP, plan, tw);
-  for (int idx = threadIdx.x; idx < H * kColsPerCta; idx += kThreads) {
-    const int i = idx / kColsPerCta, c = idx - i * kColsPerCta;
+  for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads) {
+    const int i = idx / CPC, c = idx - i * CPC;
     if (c < nc) {
       int ii = i + half; if (ii >= H) ii -= H;
       d_c[(size_t)i * W + l0 + c] = adj[c * HP + ii];
@@ -194,15 +218,13 @@ __device__ __forceinline__ float2 fetch(const float2* __restrict__ img, int y, i
 
 // One CTA per (row i, group m): resample row i of the image along group m's deformed grid into
 // shared memory, then evaluate the row DFT only at the group's phase-encode lines.
-__global__ void __launch_bounds__(kThreads)
-motion_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ disp,
-                       const float2* __restrict__ ident, const __grid_constant__ immoco_lines lines,
-                       const float2* __restrict__ tw_g, float2* __restrict__ c_out, int H, int W) {
-  pdl_wait();
+__device__ __forceinline__ void motion_rows_fwd_body(const float2* __restrict__ image, const float2* __restrict__ disp,
+                                                     const float2* __restrict__ ident, const immoco_lines& lines,
+                                                     const float2* __restrict__ tw_g, float2* __restrict__ c_out,
+                                                     int H, int W, int i, int m) {
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* row = tw + W;
-  const int i = blockIdx.x, m = blockIdx.y;
   const int l_beg = __ldg(lines.group_ofs + m), l_end = __ldg(lines.group_ofs + m + 1);
   if (l_beg == l_end) return;
   for (int t = threadIdx.x; t < W; t += kThreads) tw[t] = __ldg(tw_g + t);
@@ -240,20 +262,42 @@ motion_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restric
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+motion_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ disp,
+                       const float2* __restrict__ ident, const __grid_constant__ immoco_lines lines,
+                       const float2* __restrict__ tw_g, float2* __restrict__ c_out, int H, int W) {
+  pdl_wait();
+  motion_rows_fwd_body(image, disp, ident, lines, tw_g, c_out, H, W, blockIdx.x, blockIdx.y);
+}
+
+// Fused row launch of the fit loop: blockIdx.y == 0 -> static row pass (2 rows per CTA, result ADDED into
+// c_out, zero-weight lines skipped); blockIdx.y == 1 + m -> pruned rows of movement group m.  c_out must be
+// zero on entry (colpass_loss_kernel re-zeroes it after loading).  One launch instead of two dependent ones.
+__global__ void __launch_bounds__(kThreads)
+rows_fwd_fused_kernel(const float2* __restrict__ image, const float2* __restrict__ disp,
+                      const float2* __restrict__ ident, const __grid_constant__ immoco_lines lines,
+                      const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
+                      float2* __restrict__ c_out, int H, int W) {
+  pdl_wait();
+  if (blockIdx.y == 0) {
+    if ((int)blockIdx.x * kRowsPerCta >= H) return;
+    rows_body<false, true>(image, c_out, H, W, plan, tw_g, nullptr, lines.static_w, 1.0f, 0, blockIdx.x);
+  } else {
+    motion_rows_fwd_body(image, disp, ident, lines, tw_g, c_out, H, W, blockIdx.x, (int)blockIdx.y - 1);
+  }
+}
+
 // Adjoint of the kernel above: pruned inverse row DFT -> d(moved row) -> scatter into d_image
 // (grid_sampler_2d_backward) and the cotangent of the PRE-tanh displacement.
-__global__ void __launch_bounds__(kThreads)
-motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict__ image,
-                       const float2* __restrict__ disp, const float2* __restrict__ ident,
-                       const __grid_constant__ immoco_lines lines, const float2* __restrict__ tw_g,
-                       float2* __restrict__ d_image, float2* __restrict__ d_disp, int pre_tanh, int H,
-                       int W) {
-  pdl_wait();
+__device__ __forceinline__ void motion_rows_bwd_body(const float2* __restrict__ d_c, const float2* __restrict__ image,
+                                                     const float2* __restrict__ disp, const float2* __restrict__ ident,
+                                                     const immoco_lines& lines, const float2* __restrict__ tw_g,
+                                                     float2* __restrict__ d_image, float2* __restrict__ d_disp,
+                                                     int pre_tanh, int H, int W, int i, int m) {
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* gl = tw + W;
   int* la = reinterpret_cast<int*>(gl + lines.max_lines);
-  const int i = blockIdx.x, m = blockIdx.y;
   const int l_beg = __ldg(lines.group_ofs + m), l_end = __ldg(lines.group_ofs + m + 1);
   const int nl = l_end - l_beg;
   const int half = W >> 1;
@@ -319,6 +363,34 @@ motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict_
     const float sx = pre_tanh ? (1.0f - d.x * d.x) : 1.0f;
     const float sy = pre_tanh ? (1.0f - d.y * d.y) : 1.0f;
     d_disp[base + j] = make_float2(sx * (mx * gix), sy * (my * giy));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict__ image,
+                       const float2* __restrict__ disp, const float2* __restrict__ ident,
+                       const __grid_constant__ immoco_lines lines, const float2* __restrict__ tw_g,
+                       float2* __restrict__ d_image, float2* __restrict__ d_disp, int pre_tanh, int H,
+                       int W) {
+  pdl_wait();
+  motion_rows_bwd_body(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, pre_tanh, H, W, blockIdx.x, blockIdx.y);
+}
+
+// Fused adjoint row launch of the fit loop: blockIdx.y == 0 -> adjoint static row pass, ADDED into d_image
+// with float atomics; blockIdx.y == 1 + m -> adjoint of movement group m (scatter into d_image, d_disp).
+__global__ void __launch_bounds__(kThreads)
+rows_bwd_fused_kernel(const float2* __restrict__ d_c, const float2* __restrict__ image,
+                      const float2* __restrict__ disp, const float2* __restrict__ ident,
+                      const __grid_constant__ immoco_lines lines, const __grid_constant__ FftPlan plan,
+                      const float2* __restrict__ tw_g, float2* __restrict__ d_image,
+                      float2* __restrict__ d_disp, int H, int W) {
+  pdl_wait();
+  if (blockIdx.y == 0) {
+    if ((int)blockIdx.x * kRowsPerCta >= H) return;
+    rows_body<true, true>(d_c, d_image, H, W, plan, tw_g, lines.static_w, nullptr, 1.0f, 1, blockIdx.x);
+  } else {
+    motion_rows_bwd_body(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, 1, H, W, blockIdx.x,
+                         (int)blockIdx.y - 1);
   }
 }
 
@@ -517,20 +589,38 @@ extern "C" int immoco_forward_model_bwd(const float* d_k, const float* image, co
   return launch_motion_bwd(c_tmp, image, disp, ident, lines, tw_w, d_image, d_disp, pre_tanh, h, w, s);
 }
 
-extern "C" int immoco_colpass_loss(const float* c, const float* k_in, float* k_out, float* d_c,
-                                   double* loss_acc, const float* tw_h, int32_t h, int32_t w,
-                                   void* stream) {
+static int colpass_launch(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
+                          const float* tw_h, int32_t h, int32_t w, float* zero_after_load, void* stream) {
   const Plans p = make_plans(h, w);
   if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
   const size_t smem = cols_smem(h);
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
-  allow_smem(colpass_loss_kernel, smem);
-  const int grid = (w + kColsPerCta - 1) / kColsPerCta;
-  immoco_launch(colpass_loss_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, 
-      (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
-      (const float2*)tw_h);
+  if ((w + kColsPerCta - 1) / kColsPerCta >= IMMOCO_NUM_SMS) {
+    allow_smem(colpass_loss_kernel<kColsPerCta>, smem);
+    const int grid = (w + kColsPerCta - 1) / kColsPerCta;
+    immoco_launch(colpass_loss_kernel<kColsPerCta>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream,
+        (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
+        (const float2*)tw_h, (float2*)zero_after_load);
+  } else {       // narrow images (320 columns -> 80 CTAs of 4): 2 columns per CTA so every SM has work
+    allow_smem(colpass_loss_kernel<2>, smem);
+    const int grid = (w + 1) / 2;
+    immoco_launch(colpass_loss_kernel<2>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream,
+        (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
+        (const float2*)tw_h, (float2*)zero_after_load);
+  }
   IMMOCO_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int immoco_colpass_loss(const float* c, const float* k_in, float* k_out, float* d_c,
+                                   double* loss_acc, const float* tw_h, int32_t h, int32_t w,
+                                   void* stream) {
+  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, nullptr, stream);
+}
+// fit.cu: column pass that leaves its input buffer zeroed for the next iteration's fused row launch
+int immoco_colpass_loss_zero(float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
+                             const float* tw_h, int h, int w, void* stream) {
+  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, c, stream);
 }
 
 extern "C" int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc,
@@ -562,4 +652,36 @@ int immoco_motion_rows_bwd(const float* d_c, const float* image, const float* di
                            const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp,
                            int h, int w, void* stream) {
   return launch_motion_bwd(d_c, image, disp, ident, lines, tw_w, d_image, d_disp, 1, h, w, (cudaStream_t)stream);
+}
+
+// Fused row launches of the fit loop (fit.cu).  c_out must be zero on entry of the forward one.
+int immoco_rows_fwd_fused(const float* image, const float* disp, const float* ident, const immoco_lines* lines,
+                          const float* tw_w, float* c_out, int h, int w, void* stream) {
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(w + 2 * kRowsPerCta * w) * sizeof(float2);     // >= the motion rows' 2 W
+  if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
+  allow_smem(rows_fwd_fused_kernel, smem);
+  dim3 grid(h, 1 + lines->n_groups);
+  immoco_launch(rows_fwd_fused_kernel, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)image,
+                (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w, (float2*)c_out, h, w);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+int immoco_rows_bwd_fused(const float* d_c, const float* image, const float* disp, const float* ident,
+                          const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp, int h, int w,
+                          void* stream) {
+  const Plans p = make_plans(h, w);
+  if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  size_t smem = (size_t)(w + 2 * kRowsPerCta * w) * sizeof(float2);
+  const size_t smem_m = (size_t)w * sizeof(float2) + (size_t)lines->max_lines * (sizeof(float2) + sizeof(int));
+  if (smem_m > smem) smem = smem_m;
+  if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
+  allow_smem(rows_bwd_fused_kernel, smem);
+  dim3 grid(h, 1 + lines->n_groups);
+  immoco_launch(rows_bwd_fused_kernel, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)d_c,
+                (const float2*)image, (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w,
+                (float2*)d_image, (float2*)d_disp, h, w);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
 }

@@ -12,6 +12,24 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// table-row gather of the forward kernels.  Rows are re-used ~6x per pass but by unrelated pixels, so L1
+// never hits beyond the lane pair itself: IMMOCO_HG_LOAD selects the cache policy of the gather
+// (0: ld.global.nc, 1: ld.global.cg -- L2 only, 2: ld.global.nc.L1::no_allocate)
+#ifndef IMMOCO_HG_LOAD
+#define IMMOCO_HG_LOAD 0
+#endif
+__device__ __forceinline__ float2 load_row(const float2* p) {
+#if IMMOCO_HG_LOAD == 1
+  return __ldcg(p);
+#elif IMMOCO_HG_LOAD == 2
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreads)
 hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
@@ -198,7 +216,7 @@ __device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, 
     const float w0 = half ? frac[0] : 1.0f - frac[0];
     float2 v[1 << (D - 1)];
 #pragma unroll
-    for (int c = 0; c < (1 << (D - 1)); ++c) v[c] = __ldg(tab + pt.index(c));     // all gathers in flight
+    for (int c = 0; c < (1 << (D - 1)); ++c) v[c] = load_row(tab + pt.index(c));     // all gathers in flight
 #pragma unroll
     for (int c = 0; c < (1 << (D - 1)); ++c) {
       const float w = pair_weight<D>(frac, w0, c);
@@ -309,6 +327,14 @@ int check(const immoco_grid_desc* g, int64_t n) {
 
 static int g_pair = 1;   // 1: lane-pair kernels (product path); 0: one thread per point (A/B check)
 static int g_ctas_per_sm = 0;   // > 0: persistent pair kernels with this many 256-thread CTAs per SM; 0: one CTA per item
+// backward only (overrides g_ctas_per_sm when > 0): the scatter is paced by the L2 atomic units, not by
+// occupancy, so it can run as a thin persistent grid beside an SM-bound kernel of the other branch
+static int g_bwd_ctas_per_sm = 0;
+extern "C" int immoco_set_hashgrid_bwd_ctas_per_sm(int32_t ctas) {
+  if (ctas < 0 || ctas > 64) return IMMOCO_ERR_BAD_ARG;
+  g_bwd_ctas_per_sm = ctas;
+  return 0;
+}
 extern "C" int immoco_set_hashgrid_impl(int32_t pair) { g_pair = pair ? 1 : 0; return 0; }
 extern "C" int immoco_set_hashgrid_ctas_per_sm(int32_t ctas) {
   if (ctas < 0 || ctas > 64) return IMMOCO_ERR_BAD_ARG;
@@ -355,11 +381,16 @@ static int run_bwd(const immoco_grid_desc* grid, const float* coords, const floa
     int b = a + 1;
     const bool pair = g_pair && grid->hashed[a];
     while (b < l1 && (g_pair && grid->hashed[b]) == pair) ++b;
+    const int per_sm = g_bwd_ctas_per_sm > 0 ? g_bwd_ctas_per_sm : g_ctas_per_sm;
     dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(b - a));
+    if (per_sm > 0) {       // the dense-level kernel strides over the point tiles
+      const unsigned gx = (unsigned)((IMMOCO_NUM_SMS * per_sm + (b - a) - 1) / (b - a));
+      if (gx < g.x) g.x = gx;
+    }
     if (pair) {
       const int tiles = (int)ceil_div64(n, kPairPoints);
       const int64_t items = (int64_t)tiles * (b - a);
-      const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
+      const int64_t cap = per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * per_sm : items;
       const unsigned gp = (unsigned)(items < cap ? items : cap);
       if (grid->n_dims == 2)
         immoco_launch(hashgrid_bwd_pair_kernel<2>, dim3(gp), dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc, (float2*)grad_table, n, a, b - a, tiles);

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert getattr(native_lib, name) is not None
     assert native_lib.immoco_abi_version() == 1
-    assert native_lib.immoco_launches_per_iteration(4) == 18 and len(nat.PROFILE_SLOTS) == 16
+    assert native_lib.immoco_launches_per_iteration(4) == 16 and len(nat.PROFILE_SLOTS) == 16
     sizes = (C.c_int32 * 3)()
     native_lib.immoco_struct_sizes(sizes)
     assert tuple(sizes) == (C.sizeof(nat.GridDesc), C.sizeof(nat.Lines), C.sizeof(nat.Fit))
