@@ -238,7 +238,7 @@ def lambda_schedule(iters: int, lambda_ge: float, variant: str = "main") -> List
 
 class FitEngine:
     """Device state + native loop for ONE slice: both INRs' parameters, gradients and Adam moments
-    live in one flat fp32 vector [motion | image]; every iteration is 18 kernel launches issued by
+    live in one flat fp32 vector [motion | image]; every iteration is 16 kernel launches issued by
     ``immoco_fit_run`` with no host synchronisation."""
 
     def __init__(self, model: IMMoCo, max_iters: int):
