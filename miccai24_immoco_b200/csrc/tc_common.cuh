@@ -72,6 +72,22 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one lane of a converged warp (all 32 lanes must execute this): tells ptxas that exactly one thread issues
+// the MMAs that follow, so their operands move to uniform registers once (R2UR) instead of through a
+// per-instruction "waterfall" loop over the active lanes (ELECT + R2UR.BROADCAST x4 + BRA.U.ANY around
+// every UTCHMMA -- what `(tid & 31) == 0` compiled to)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA issue (one thread) -------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
