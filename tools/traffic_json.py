@@ -12,7 +12,8 @@ SLOT_OF = [  # (regex on the kernel name incl. template args, slots it feeds)
     (r"mlp_fwd_tc_kernel<256", ["mlp_fwd_image"]), (r"mlp_fwd_tc_kernel<64", ["mlp_fwd_motion"]),
     (r"mlp_bwd_tc_kernel<256", ["mlp_bwd_image"]), (r"mlp_bwd_tc64_kernel", ["mlp_bwd_motion"]),
     (r"fft_rows_kernel<0>|fft_rows_kernel<false>", ["fft_rows"]), (r"fft_rows_kernel<1>|fft_rows_kernel<true>", ["fft_rows_adj"]),
-    (r"motion_rows_fwd_kernel", ["motion_rows_fwd"]), (r"motion_rows_bwd_kernel", ["motion_rows_bwd"]),
+    (r"motion_rows_fwd_kernel|rows_fwd_fused_kernel", ["motion_rows_fwd"]),
+    (r"motion_rows_bwd_kernel|rows_bwd_fused_kernel", ["motion_rows_bwd"]),
     (r"colpass_loss_kernel", ["colpass_loss"]), (r"grad_entropy_kernel", ["grad_entropy"]),
     (r"adam_kernel", ["adam_motion", "adam_image"]),
 ]
