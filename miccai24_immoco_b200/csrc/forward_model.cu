@@ -16,9 +16,15 @@ constexpr int kThreads = 256;
 constexpr int kRowsPerCta = 2;   // row pass: transforms per CTA
 constexpr int kColsPerCta = 4;   // column pass: adjacent columns per CTA (64 B segments)
 
-__device__ __forceinline__ int wrap_mod(int a, int n) {
-  int r = a % n;
-  return r < 0 ? r + n : r;
+// a mod n in [0, n) without the integer-division routine (the pruned row DFTs take one per tap): the
+// quotient is estimated in fp32 and corrected by at most one step either way; exact for |a| < 2^22
+// (here |a| <= W^2 / 4)
+__device__ __forceinline__ int wrap_mod_fast(int a, int n, float inv_n) {
+  const int q = __float2int_rd((float)a * inv_n);
+  int r = a - q * n;
+  if (r < 0) r += n;
+  if (r >= n) r -= n;
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,13 +247,14 @@ __device__ __forceinline__ void motion_rows_fwd_body(const float2* __restrict__ 
   }
   __syncthreads();
   const int half = W >> 1;
+  const float inv_w = 1.0f / (float)W;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int li = l_beg + warp; li < l_end; li += kThreads / 32) {
     const int l = __ldg(lines.line_idx + li);
     const int a = l - half;
     float ax = 0.f, ay = 0.f;
     for (int j = lane; j < W; j += 32) {
-      const float2 w = tw[wrap_mod(a * (j - half), W)];
+      const float2 w = tw[wrap_mod_fast(a * (j - half), W, inv_w)];
       const float2 v = row[j];
       ax += v.x * w.x - v.y * w.y;
       ay += v.x * w.y + v.y * w.x;
@@ -312,11 +319,12 @@ __device__ __forceinline__ void motion_rows_bwd_body(const float2* __restrict__ 
   __syncthreads();
   const size_t base = ((size_t)m * H + i) * W;
   const float mx = (float)W / 2.0f, my = (float)H / 2.0f;
+  const float inv_w = 1.0f / (float)W;
   for (int j = threadIdx.x; j < W; j += kThreads) {
     const int bq = j - half;
     float gr = 0.f, gi = 0.f;   // cotangent of the moved pixel (re, im)
     for (int li = 0; li < nl; ++li) {
-      const float2 w = tw[wrap_mod(la[li] * bq, W)];
+      const float2 w = tw[wrap_mod_fast(la[li] * bq, W, inv_w)];
       const float2 g = gl[li];
       gr += g.x * w.x + g.y * w.y;     // g * conj(w)
       gi += g.y * w.x - g.x * w.y;
