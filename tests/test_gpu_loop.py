@@ -338,3 +338,46 @@ def test_reconstruct_batch_matches_single_slice_calls():
     # device-resident masks and a single slot take the same path
     one = reconstruct_batch(ks[:1], [ms[0].to(DEV)], iters, in_flight=1, image_params=pis[:1], motion_params=pms[:1])
     assert rel_l2(one[0], imgs[0]) < 5e-2
+
+
+@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (32, 32, 0)])
+def test_fused_row_launches_equal_separate_launches(h, w, n_mov):
+    """immoco_fit_run issues the static row pass and the pruned motion rows as ONE launch (forward, adjoint):
+    the first iteration's k-space, both losses and the parameters after the step must equal the four separate
+    launches to rounding (the adjoint accumulates d_image with float atomics, hence not bit-for-bit)."""
+    lib = mb.lib()
+    if n_mov > 0:
+        case = orc.make_case(h, w, n_mov, 1000)
+        masks, k = case["masks"].to(DEV), case["kspace_motion"]
+    else:
+        masks = torch.zeros((0, h, w), dtype=torch.long, device=DEV)
+        g = torch.Generator().manual_seed(5)
+        k = torch.complex(torch.randn(h, w, generator=g), torch.randn(h, w, generator=g))
+    model = mb.IMMoCo(masks)
+    p_img = model.image_inr.params.detach().clone()
+    p_mot = model.motion_inr.params.detach().clone()
+    if n_mov > 0:      # a displacement field of ~0.1 so the motion rows do real work
+        p_mot[2048:3072] *= 10.0
+        p_mot[3072:] *= 300.0
+    eng = mb.FitEngine(model, 4)
+    eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
+    lam = mb.lambda_schedule(10, 1e-2)[:4]
+    out = {}
+    try:
+        for fused in (0, 1):
+            lib.immoco_set_fused_rows(fused)
+            eng.reset(p_img, p_mot)
+            eng.run(lam, 1e-2, 0, 1)
+            torch.cuda.synchronize()
+            out[fused] = (eng.k_out.clone(), eng.loss[0].clone(), eng.params.clone(), eng.d_image.clone(),
+                          eng.d_disp.clone())
+    finally:
+        lib.immoco_set_fused_rows(1)
+    assert rel_l2(out[1][0], out[0][0]) < 2e-6                    # forward k-space
+    assert torch.allclose(out[1][1], out[0][1], rtol=1e-6)        # both loss accumulators
+    assert rel_l2(out[1][3], out[0][3]) < 1e-5                    # image cotangent (the fused adjoint's output)
+    if n_mov > 0:
+        assert rel_l2(out[1][4], out[0][4]) < 1e-5                # displacement cotangent
+    # Adam's first step is ~ lr * sign(g): entries whose gradient is a rounding-level sum may differ, the bulk
+    # of the parameters must land on the same values
+    assert float(((out[1][2] - out[0][2]).abs() > 1e-3).float().mean()) < 1e-3
