@@ -42,6 +42,15 @@ typedef struct immoco_grid_desc {
   uint32_t entries[IMMOCO_MAX_LEVELS];      /* rows of the level's table                 */
   uint32_t offset[IMMOCO_MAX_LEVELS + 1];   /* first row of each level (prefix sums)     */
   uint32_t hashed[IMMOCO_MAX_LEVELS];       /* 1: coherent-prime hash, 0: dense index    */
+  /* Physical row layout of a hashed level (0 = the reference's own layout: row = index).  Otherwise the row
+   * of hash index r is S(r): Gray code r ^ (r >> 1), then bit positions (swizzle & 0xff) and
+   * ((swizzle >> 8) & 0xff) exchanged.  S is a linear bijection on the level's index bits, so it is only a
+   * storage permutation (the fit engine permutes the table on the way in and out, `immoco.py:FitEngine`).
+   * Why: the two dim-0 corners of a cell are indices r and r ^ (2^t - 1); the Gray code turns that into ONE
+   * flipped bit (t - 1), and the exchange moves the one group whose t is large (coordinate +1: t = log2(res)
+   * + 1) into the low bits, so both corners of every lane pair lie in one 128-byte line.
+   * Used for power-of-two hashed levels only; ignored elsewhere. */
+  uint32_t swizzle[IMMOCO_MAX_LEVELS];
 } immoco_grid_desc;
 
 /* Column structure of the movement-group masks (src/utils/motion_utils.py:56-109 produces masks

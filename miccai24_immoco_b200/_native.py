@@ -34,6 +34,7 @@ class GridDesc(C.Structure):
         ("entries", C.c_uint32 * MAX_LEVELS),
         ("offset", C.c_uint32 * (MAX_LEVELS + 1)),
         ("hashed", C.c_uint32 * MAX_LEVELS),
+        ("swizzle", C.c_uint32 * MAX_LEVELS),
     ]
 
 

@@ -48,9 +48,19 @@ __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a 
 // hash-grid index maths (tiny-cuda-nn grid.h grid_index / coherent-prime hash, restated in
 // oracle/immoco_oracle.py:grid_corner_index).  All arithmetic is uint32 and wraps.
 // ---------------------------------------------------------------------------------------------
+// physical row of hash index r under immoco_grid_desc::swizzle (0: identity): Gray code, then two bit
+// positions exchanged -- a linear bijection on the index bits
+__host__ __device__ __forceinline__ uint32_t grid_swizzle(uint32_t r, uint32_t swz) {
+  if (swz == 0u) return r;
+  r ^= r >> 1;
+  const uint32_t a = swz & 0xffu, b = (swz >> 8) & 0xffu;
+  const uint32_t x = ((r >> a) ^ (r >> b)) & 1u;
+  return r ^ ((x << a) | (x << b));
+}
+
 template <int D>
 __host__ __device__ __forceinline__ uint32_t grid_index(const uint32_t (&q)[D], uint32_t hashed,
-                                                        uint32_t entries, uint32_t res) {
+                                                        uint32_t entries, uint32_t res, uint32_t swz = 0u) {
   uint32_t idx;
   if (hashed) {
     idx = q[0];  // prime 1
@@ -67,7 +77,9 @@ __host__ __device__ __forceinline__ uint32_t grid_index(const uint32_t (&q)[D], 
   }
   // entries is a power of two for every level of the reference configuration; keep the general
   // modulo for others (round-up-to-8 dense levels of odd resolutions).
-  return ((entries & (entries - 1)) == 0) ? (idx & (entries - 1)) : (idx % entries);
+  if ((entries & (entries - 1)) != 0) return idx % entries;
+  idx &= entries - 1;
+  return (hashed && swz) ? grid_swizzle(idx, swz) : idx;
 }
 
 // pos = fmaf(scale, x, 0.5); cell = (uint32)(int)floor(pos); frac = pos - floor(pos)

@@ -40,6 +40,7 @@ hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
   const uint32_t res = g.resolution[level];
   const uint32_t entries = g.entries[level];
   const uint32_t hashed = g.hashed[level];
+  const uint32_t swz = g.swizzle[level];
   const float2* __restrict__ tab = table + g.offset[level];
 
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -60,7 +61,7 @@ hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
         // same association order as the oracle: w = w0 * w1 * w2
         w = (d == 0) ? (bit ? frac[0] : 1.0f - frac[0]) : w * (bit ? frac[d] : 1.0f - frac[d]);
       }
-      const float2 v = __ldg(tab + grid_index<D>(q, hashed, entries, res));
+      const float2 v = __ldg(tab + grid_index<D>(q, hashed, entries, res, swz));
       acc.x = fmaf(w, v.x, acc.x);
       acc.y = fmaf(w, v.y, acc.y);
     }
@@ -83,6 +84,7 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
   const uint32_t res = g.resolution[level];
   const uint32_t entries = g.entries[level];
   const uint32_t hashed = g.hashed[level];
+  const uint32_t swz = g.swizzle[level];
   float2* __restrict__ gtab = grad_table + g.offset[level];
   const unsigned lane = threadIdx.x & 31u;
 
@@ -111,7 +113,7 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
         q[d] = cell[d] + (uint32_t)bit;
         w = (d == 0) ? (bit ? frac[0] : 1.0f - frac[0]) : w * (bit ? frac[d] : 1.0f - frac[d]);
       }
-      const uint32_t idx = grid_index<D>(q, hashed, entries, res);
+      const uint32_t idx = grid_index<D>(q, hashed, entries, res, swz);
       float vx = w * go.x, vy = w * go.y;
       if (hashed) {
         // one 64-bit vector reduction per corner (RED.ADD.F32x2)
@@ -156,11 +158,11 @@ enum { kIdxHash = 0, kIdxDense = 1, kIdxAny = 2 };
 template <int D, int MODE>
 struct PairTerms {
   uint32_t t[D][2];     // t[d][bit]: contribution of corner bit `bit` of dimension d (d >= 1)
-  uint32_t q0, mask, entries, res, hashed;
+  uint32_t q0, mask, entries, res, hashed, swz;
   uint32_t cell[D];
   __device__ __forceinline__ void init(const uint32_t (&c)[D], int half, uint32_t entries_, uint32_t res_,
-                                       uint32_t hashed_) {
-    entries = entries_; res = res_; hashed = hashed_; mask = entries_ - 1u;
+                                       uint32_t hashed_, uint32_t swz_) {
+    entries = entries_; res = res_; hashed = hashed_; mask = entries_ - 1u; swz = swz_;
     q0 = c[0] + (uint32_t)half;
     uint32_t mul = 1u;
 #pragma unroll
@@ -179,7 +181,7 @@ struct PairTerms {
       q[0] = q0;
 #pragma unroll
       for (int d = 1; d < D; ++d) q[d] = cell[d] + (uint32_t)((c >> (d - 1)) & 1);
-      return grid_index<D>(q, hashed, entries, res);
+      return grid_index<D>(q, hashed, entries, res, swz);
     }
     uint32_t idx = q0;      // prime 1 / stride 1
 #pragma unroll
@@ -187,7 +189,8 @@ struct PairTerms {
       const uint32_t term = t[d][(c >> (d - 1)) & 1];
       idx = (MODE == kIdxHash) ? (idx ^ term) : (idx + term);
     }
-    return idx & mask;
+    idx &= mask;
+    return (MODE == kIdxHash) ? grid_swizzle(idx, swz) : idx;
   }
 };
 
@@ -202,7 +205,7 @@ __device__ __forceinline__ float pair_weight(const float (&frac)[D], float w0, i
 template <int D, int MODE>
 __device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, const float2* __restrict__ tab,
                                               float2* __restrict__ enc_level, int n, int base, float scale,
-                                              uint32_t res, uint32_t entries, uint32_t hashed) {
+                                              uint32_t res, uint32_t entries, uint32_t hashed, uint32_t swz) {
   const int half = threadIdx.x & 1;
   const int i = base + (threadIdx.x >> 1);
   float2 acc = make_float2(0.f, 0.f);
@@ -212,7 +215,7 @@ __device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, 
 #pragma unroll
     for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
     PairTerms<D, MODE> pt;
-    pt.init(cell, half, entries, res, hashed);
+    pt.init(cell, half, entries, res, hashed, swz);
     const float w0 = half ? frac[0] : 1.0f - frac[0];
     float2 v[1 << (D - 1)];
 #pragma unroll
@@ -247,16 +250,17 @@ hashgrid_fwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float
     const float2* __restrict__ tab = table + g.offset[level];
     float2* __restrict__ out = enc + (size_t)level * n;
     const bool pow2 = (entries & (entries - 1u)) == 0u;
-    if (pow2 && hashed) fwd_pair_item<D, kIdxHash>(coords, tab, out, n, base, scale, res, entries, hashed);
-    else if (pow2) fwd_pair_item<D, kIdxDense>(coords, tab, out, n, base, scale, res, entries, hashed);
-    else fwd_pair_item<D, kIdxAny>(coords, tab, out, n, base, scale, res, entries, hashed);
+    const uint32_t swz = g.swizzle[level];
+    if (pow2 && hashed) fwd_pair_item<D, kIdxHash>(coords, tab, out, n, base, scale, res, entries, hashed, swz);
+    else if (pow2) fwd_pair_item<D, kIdxDense>(coords, tab, out, n, base, scale, res, entries, hashed, 0u);
+    else fwd_pair_item<D, kIdxAny>(coords, tab, out, n, base, scale, res, entries, hashed, 0u);
   }
 }
 
 template <int D, int MODE>
 __device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, const float2* __restrict__ d_enc_level,
                                               float2* __restrict__ gtab, int n, int base, float scale,
-                                              uint32_t res, uint32_t entries) {
+                                              uint32_t res, uint32_t entries, uint32_t swz) {
   const int half = threadIdx.x & 1;
   const int i = base + (threadIdx.x >> 1);
   float2 go = make_float2(0.f, 0.f);
@@ -271,12 +275,13 @@ __device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, 
   }
   const bool live = !(go.x == 0.0f && go.y == 0.0f);      // adding +-0 is a no-op (also covers i >= n)
   PairTerms<D, MODE> pt;
-  pt.init(cell, half, entries, res, 1u);
+  pt.init(cell, half, entries, res, 1u, swz);
   const float w0 = half ? frac[0] : 1.0f - frac[0];
-  // Even base cell (hash prime 1 on dimension 0): the two lanes' rows are idx and idx ^ 1, one aligned
-  // 16-byte slot -> ONE 128-bit reduction (RED.ADD.F32x4) issued by the even lane instead of two 64-bit
-  // ones.  Both lanes of a pair hold the same point, so the predicate is pair-uniform.
-  const bool merge = (MODE == kIdxHash) && ((cell[0] & 1u) == 0u);
+  // The two lanes' hash indices differ by X = cell ^ (cell + 1) (hash prime 1 on dimension 0); the row layout
+  // S is linear, so their rows differ by S(X).  S(X) == 1 (reference layout: even base cell): the rows are
+  // idx and idx ^ 1, one aligned 16-byte slot -> ONE 128-bit reduction (RED.ADD.F32x4) issued by the even
+  // lane instead of two 64-bit ones.  Both lanes of a pair hold the same point: the predicate is pair-uniform.
+  const bool merge = (MODE == kIdxHash) && (grid_swizzle((cell[0] ^ (cell[0] + 1u)) & (entries - 1u), swz) == 1u);
 #pragma unroll
   for (int c = 0; c < (1 << (D - 1)); ++c) {
     const float w = pair_weight<D>(frac, w0, c);
@@ -311,8 +316,8 @@ hashgrid_bwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float
     const uint32_t entries = g.entries[level];
     float2* __restrict__ gtab = grad_table + g.offset[level];
     const float2* __restrict__ go = d_enc + (size_t)level * n;
-    if ((entries & (entries - 1u)) == 0u) bwd_pair_item<D, kIdxHash>(coords, go, gtab, n, base, scale, res, entries);
-    else bwd_pair_item<D, kIdxAny>(coords, go, gtab, n, base, scale, res, entries);
+    if ((entries & (entries - 1u)) == 0u) bwd_pair_item<D, kIdxHash>(coords, go, gtab, n, base, scale, res, entries, g.swizzle[level]);
+    else bwd_pair_item<D, kIdxAny>(coords, go, gtab, n, base, scale, res, entries, 0u);
   }
 }
 

@@ -39,7 +39,9 @@ class GridSpec:
     def n_table_params(self) -> int:
         return self.offsets[-1] * 2
 
-    def desc(self) -> nat.GridDesc:
+    def desc(self, swizzle: Tuple[int, ...] = ()) -> nat.GridDesc:
+        """C-ABI descriptor; ``swizzle`` (one word per level, see ``row_swizzle``) selects the physical row
+        layout of the hashed levels -- empty = the reference's own layout."""
         d = nat.GridDesc()
         d.n_dims = self.n_dims
         d.n_levels = self.n_levels
@@ -48,9 +50,54 @@ class GridSpec:
             d.resolution[i] = self.resolutions[i]
             d.entries[i] = self.entries[i]
             d.hashed[i] = self.hashed[i]
+            d.swizzle[i] = int(swizzle[i]) if swizzle else 0
         for i in range(self.n_levels + 1):
             d.offset[i] = self.offsets[i]
         return d
+
+    def row_swizzle(self, dim0_values) -> Tuple[int, ...]:
+        """Row layout of the hashed levels for inputs whose FIRST coordinate only takes the few values
+        ``dim0_values`` (the Motion INR: one value per movement group, src/models/immoco.py:48-53).
+
+        The two dim-0 corners of a cell are the hash indices r and r ^ X, X = cell ^ (cell + 1) = 2^t - 1.
+        For t <= 4 both rows share a 128-byte line; the group at coordinate +1 has cell = res - 1, i.e.
+        t = log2(res) + 1, and its two corners are far apart.  The layout word asks the kernels to store
+        row r at S(r) = swap_{a,b}(r ^ (r >> 1)): the Gray code maps every X = 2^t - 1 to the single bit
+        t - 1, and the swap moves the large t - 1 (a) to a free low position (b), so all lane pairs of the
+        level read / reduce two rows of ONE line.  0 = keep the reference's layout (nothing to gain)."""
+        words = []
+        for lvl in range(self.n_levels):
+            n = self.entries[lvl]
+            word = 0
+            if self.hashed[lvl] and (n & (n - 1)) == 0 and len(dim0_values) > 0:
+                tops = []
+                for u in dim0_values:
+                    pos = np.float32(np.float64(np.float32(self.scales[lvl])) * np.float64(np.float32(u)) + 0.5)
+                    cell = int(np.floor(pos)) & 0xFFFFFFFF
+                    x = (cell ^ ((cell + 1) & 0xFFFFFFFF)) & (n - 1)
+                    tops.append(x.bit_length() - 1)
+                small = {t for t in tops if t < 4}
+                big = sorted({t for t in tops if t >= 4}, key=lambda t: -tops.count(t))
+                free = [b for b in range(4) if b not in small]
+                if big and free:
+                    word = (1 << 31) | (free[0] << 8) | big[0]
+            words.append(word)
+        return tuple(words)
+
+    def row_permutation(self, swizzle: Tuple[int, ...]) -> np.ndarray:
+        """perm[r] = physical row of logical (reference-layout) row r, over the whole table."""
+        perm = np.arange(self.n_rows, dtype=np.int64)
+        for lvl in range(self.n_levels):
+            w = int(swizzle[lvl]) if swizzle else 0
+            if w == 0 or not self.hashed[lvl] or (self.entries[lvl] & (self.entries[lvl] - 1)) != 0:
+                continue
+            r = np.arange(self.entries[lvl], dtype=np.int64)
+            r ^= r >> 1
+            a, b = w & 0xFF, (w >> 8) & 0xFF
+            x = ((r >> a) ^ (r >> b)) & 1
+            r ^= (x << a) | (x << b)
+            perm[self.offsets[lvl]: self.offsets[lvl + 1]] = self.offsets[lvl] + r
+        return perm
 
 
 def grid_spec(n_dims: int, cfg: dict) -> GridSpec:

@@ -236,12 +236,28 @@ def lambda_schedule(iters: int, lambda_ge: float, variant: str = "main") -> List
     return lams
 
 
+_ROW_PERM_CACHE: dict = {}
+
+
+def _row_permutation(grid, swizzle, dev) -> torch.Tensor:
+    """Device copy of ``GridSpec.row_permutation`` (one per device and layout, shared by all engines)."""
+    key = (str(dev), grid.n_dims, grid.offsets, swizzle)
+    if key not in _ROW_PERM_CACHE:
+        _ROW_PERM_CACHE[key] = torch.from_numpy(grid.row_permutation(swizzle)).to(dev)
+    return _ROW_PERM_CACHE[key]
+
+
 class FitEngine:
     """Device state + native loop for ONE slice: both INRs' parameters, gradients and Adam moments
     live in one flat fp32 vector [motion | image]; every iteration is 16 kernel launches issued by
-    ``immoco_fit_run`` with no host synchronisation."""
+    ``immoco_fit_run`` with no host synchronisation.
 
-    def __init__(self, model: IMMoCo, max_iters: int):
+    The motion grid's hashed levels are stored in a permuted ROW LAYOUT (``GridSpec.row_swizzle``: both
+    dim-0 corners of every lane pair in one 128-byte line; Adam is element-wise, so it does not care).
+    Parameters are permuted on the way in (constructor, ``reset``) and back in ``write_back``; everything
+    outside the engine sees the reference's layout.  ``row_swizzle=False`` keeps the reference layout."""
+
+    def __init__(self, model: IMMoCo, max_iters: int, row_swizzle: bool = True):
         self.model = model
         dev = model.device
         h, w, m = model.x, model.num_lines, model.num_movements
@@ -250,7 +266,17 @@ class FitEngine:
         self.n_motion, self.n_image = mot.n_params, img.n_params
         n = self.n_motion + self.n_image
         self.params = torch.empty(n, dtype=torch.float32, device=dev)
-        self.params[: self.n_motion].copy_(mot.params.detach())
+        # physical row layout of the motion table (first coordinate = one value per movement group)
+        self._swizzle: Tuple[int, ...] = ()
+        self._perm: Optional[torch.Tensor] = None
+        self._n_mlp_motion = mot.mlp.n_params
+        if row_swizzle and m > 0:
+            u = torch.unique(model.input_grid[:, 0]).cpu().numpy()
+            swz = mot.grid.row_swizzle(u) if u.size <= 64 else ()
+            if any(swz):
+                self._swizzle = swz
+                self._perm = _row_permutation(mot.grid, swz, dev)
+        self._load_motion(mot.params.detach())
         self.params[self.n_motion:].copy_(img.params.detach())
         self.state = torch.zeros((3, n), dtype=torch.float32, device=dev)   # grads, exp_avg, exp_avg_sq
         f32 = dict(dtype=torch.float32, device=dev)
@@ -273,7 +299,7 @@ class FitEngine:
         self.coords_motion = model.input_grid.contiguous() if m > 0 else torch.zeros((1, 3), **f32)
         f = nat.Fit()
         f.h, f.w, f.m = h, w, m
-        f.grid_image, f.grid_motion = img.grid.desc(), mot.grid.desc()
+        f.grid_image, f.grid_motion = img.grid.desc(), mot.grid.desc(self._swizzle)
         f.width_image, f.act_image = img.mlp.width, img.mlp.act
         f.width_motion, f.act_motion = mot.mlp.width, mot.mlp.act
         f.n_motion, f.n_image = self.n_motion, self.n_image
@@ -299,9 +325,27 @@ class FitEngine:
     def set_kspace(self, k_in: torch.Tensor) -> None:
         self.k_in.copy_(torch.view_as_real(k_in.to(torch.complex64)))
 
+    def _load_motion(self, motion_params: torch.Tensor) -> None:
+        """Reference-layout motion parameters [W1 | W2 | table] -> the engine's (permuted-row) storage."""
+        dst = self.params[: self.n_motion]
+        if self._perm is None:
+            dst.copy_(motion_params)
+            return
+        k = self._n_mlp_motion
+        dst[:k].copy_(motion_params[:k])
+        dst[k:].view(-1, 2).index_copy_(0, self._perm, motion_params[k:].to(dst.device).view(-1, 2))
+
+    def motion_params(self) -> torch.Tensor:
+        """The motion INR's parameters in the reference layout (a copy)."""
+        src = self.params[: self.n_motion]
+        if self._perm is None:
+            return src.clone()
+        k = self._n_mlp_motion
+        return torch.cat([src[:k], src[k:].view(-1, 2)[self._perm].reshape(-1)])
+
     def reset(self, image_params: torch.Tensor, motion_params: torch.Tensor) -> None:
         """Fresh instance: initial INR parameters, zero gradients / Adam moments / loss trace."""
-        self.params[: self.n_motion].copy_(motion_params)
+        self._load_motion(motion_params)
         self.params[self.n_motion:].copy_(image_params)
         self.state.zero_()
         self.loss.zero_()
@@ -329,7 +373,7 @@ class FitEngine:
 
     def write_back(self) -> None:
         with torch.no_grad():
-            self.model.motion_inr.params.copy_(self.params[: self.n_motion])
+            self.model.motion_inr.params.copy_(self.motion_params())
             self.model.image_inr.params.copy_(self.params[self.n_motion:])
 
 

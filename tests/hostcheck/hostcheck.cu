@@ -52,8 +52,8 @@ extern "C" int hostcheck_taps(const immoco_grid_desc* g, int level, const float*
         ww = (d == 0) ? (bit ? frac[0] : 1.0f - frac[0]) : ww * (bit ? frac[d] : 1.0f - frac[d]);
       }
       const uint32_t id = (D == 2)
-          ? grid_index<2>(q2, g->hashed[level], g->entries[level], g->resolution[level])
-          : grid_index<3>(q3, g->hashed[level], g->entries[level], g->resolution[level]);
+          ? grid_index<2>(q2, g->hashed[level], g->entries[level], g->resolution[level], g->swizzle[level])
+          : grid_index<3>(q3, g->hashed[level], g->entries[level], g->resolution[level], g->swizzle[level]);
       idx[(size_t)c * n + i] = id;
       w[(size_t)c * n + i] = ww;
     }

@@ -381,3 +381,33 @@ def test_fused_row_launches_equal_separate_launches(h, w, n_mov):
     # Adam's first step is ~ lr * sign(g): entries whose gradient is a rounding-level sum may differ, the bulk
     # of the parameters must land on the same values
     assert float(((out[1][2] - out[0][2]).abs() > 1e-3).float().mean()) < 1e-3
+
+
+def test_engine_row_swizzle_equals_reference_layout():
+    """FitEngine with the permuted motion-table layout vs row_swizzle=False: same forward, same losses, and
+    the same parameters (reference layout) after three steps, up to the rounding of float atomics."""
+    case = orc.make_case(64, 48, 4, 1000)
+    masks, k = case["masks"].to(DEV), case["kspace_motion"]
+    model = mb.IMMoCo(masks)
+    p_img = model.image_inr.params.detach().clone()
+    p_mot = model.motion_inr.params.detach().clone()
+    p_mot[2048:3072] *= 10.0
+    p_mot[3072:] *= 300.0
+    lam = mb.lambda_schedule(10, 1e-2)[:3]
+    out = {}
+    for swz in (False, True):
+        eng = mb.FitEngine(model, 3, row_swizzle=swz)
+        assert bool(eng._swizzle) == swz
+        eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
+        eng.reset(p_img, p_mot)
+        assert torch.equal(eng.motion_params(), p_mot)              # in and out again: exact
+        eng.run(lam, 1e-2, 0, 1)
+        torch.cuda.synchronize()
+        first = (eng.k_out.clone(), eng.loss[0].clone())
+        eng.run(lam, 1e-2, 1, 3)
+        torch.cuda.synchronize()
+        out[swz] = first + (eng.motion_params(), eng.loss_trace(lam))
+    assert rel_l2(out[True][0], out[False][0]) < 1e-6
+    assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
+    assert np.allclose(out[True][3], out[False][3], rtol=1e-4)
+    assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < 1e-3

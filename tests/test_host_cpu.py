@@ -184,3 +184,33 @@ def test_hash_index_maths_bit_exact_vs_oracle(hostcheck, dims):
         oi, ow = orc.hashgrid_taps(coords, lv, level)
         assert np.array_equal(idx.astype(np.int64), oi.numpy()), level
         assert np.array_equal(w, ow.numpy()), level
+
+
+def test_row_swizzle_is_a_storage_permutation(hostcheck):
+    """The physical row layout of the motion grid (GridSpec.row_swizzle / immoco_grid_desc::swizzle): the
+    kernels' index routine under the layout word equals the oracle's index pushed through the host-side
+    permutation, the permutation is a bijection per level, and both dim-0 corners of every tap pair end up in
+    one 128-byte line (16 rows) -- the reason for the layout."""
+    gs = grid_spec(3, mb.encoding_config)
+    lv = orc.make_grid_levels(3, orc.ENCODING_CONFIG)
+    for m in (2, 4, 5, 8):
+        coords = orc.make_grids((m, 6, 5)).contiguous()
+        u = np.unique(coords[:, 0].numpy())
+        swz = gs.row_swizzle(u)
+        assert all(w == 0 for lvl, w in enumerate(swz) if not gs.hashed[lvl]) and any(swz)
+        perm = gs.row_permutation(swz)
+        assert np.array_equal(np.sort(perm), np.arange(gs.n_rows))
+        d = gs.desc(swz)
+        n, cn = coords.shape[0], coords.numpy()
+        for level in range(16):
+            idx = np.empty((8, n), np.uint32)
+            w = np.empty((8, n), np.float32)
+            hostcheck.hostcheck_taps(C.byref(d), level, cn.ctypes.data_as(C.c_void_p), n,
+                                     idx.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p))
+            oi, _ = orc.hashgrid_taps(coords, lv, level)
+            off = gs.offsets[level]
+            want = perm[off + oi.numpy()] - off
+            assert np.array_equal(idx.astype(np.int64), want), (m, level)
+            if gs.hashed[level]:
+                # corner c and c ^ 1 differ in the dim-0 bit: same 16-row line after the permutation
+                assert np.array_equal(idx[0::2] >> 4, idx[1::2] >> 4), (m, level)
