@@ -256,6 +256,10 @@ int immoco_launches_per_iteration(int32_t m);
  * launch forward and ONE launch for the adjoint (16 launches per iteration); 0: four separate launches
  * (18 per iteration; A/B check -- results agree to rounding). */
 int immoco_set_fused_rows(int32_t on);
+/* 1 (default): inside immoco_fit_run Adam leaves the gradients in place and one memset of the gradient vector
+ * runs on a third stream during the motion chain's SM-bound stretch (the memory system is idle there);
+ * 0: Adam zeroes the gradients itself.  Results are identical. */
+int immoco_set_deferred_zero(int32_t on);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,7 @@ _SIGNATURES = {
     "immoco_set_branch_overlap": (C.c_int, [C.c_int32]),
     "immoco_set_pdl": (C.c_int, [C.c_int32]),
     "immoco_set_fused_rows": (C.c_int, [C.c_int32]),
+    "immoco_set_deferred_zero": (C.c_int, [C.c_int32]),
     "immoco_abi_version": (C.c_int, []),
     "immoco_launches_per_iteration": (C.c_int, [C.c_int32]),
     "immoco_struct_sizes": (None, [C.POINTER(C.c_int32)]),

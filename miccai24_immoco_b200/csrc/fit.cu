@@ -253,6 +253,9 @@ struct AuxStream {
   cudaStream_t owner = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join_fwd = nullptr, mlp_done = nullptr, join_end = nullptr;
+  // deferred gradient zeroing (see immoco_fit_run): a third stream and its events
+  cudaStream_t zero_stream = nullptr;
+  cudaEvent_t adam_i_done = nullptr, zero_start = nullptr, zero_done = nullptr;
 };
 static std::mutex g_aux_mutex;
 static int g_aux_high_priority = 1;
@@ -275,13 +278,19 @@ static AuxStream* aux_for(cudaStream_t owner) {
   if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, g_aux_high_priority ? prio_hi : prio_lo) !=
       cudaSuccess)
     return nullptr;
-  cudaEvent_t* ev[4] = {&a.fork, &a.join_fwd, &a.mlp_done, &a.join_end};
+  if (cudaStreamCreateWithPriority(&a.zero_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
+  cudaEvent_t* ev[7] = {&a.fork, &a.join_fwd, &a.mlp_done, &a.join_end, &a.adam_i_done, &a.zero_start, &a.zero_done};
   for (auto e : ev)
     if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   table[used] = a;
   return &table[used++];
 }
 static int g_overlap = 1, g_profile_overlap = 0;
+// 1 (default): Adam leaves the gradients in place and ONE memset of the whole gradient vector runs on a third
+// stream while the motion chain is in its SM-bound stretch (MLP forward, row / column passes), i.e. when the
+// memory system is idle; 0: Adam zeroes the gradients itself (4 more bytes per parameter on the critical path)
+static int g_deferred_zero = 1;
+extern "C" int immoco_set_deferred_zero(int32_t on) { g_deferred_zero = on ? 1 : 0; return 0; }
 extern "C" int immoco_set_branch_overlap(int32_t on) { g_overlap = on ? 1 : 0; return 0; }
 // 1: instrumented iterations keep the two-stream schedule (timeline mode); 0 (default): they run
 // serially on the caller's stream so per-kernel durations are contention-free.
@@ -317,6 +326,7 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
   cudaStream_t ms = (cudaStream_t)stream;
   AuxStream* aux = (g_overlap && M > 0) ? aux_for(ms) : nullptr;
   bool forked = false;          // aux currently carries work that `ms` has not joined
+  bool zero_pending = false;    // the previous iteration left its gradients for the deferred memset
 
   const bool fuse_rows = g_fuse_rows != 0;
   // the fused row launch ADDS into c_tmp; the column pass re-zeroes it for the next iteration
@@ -341,6 +351,13 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
       forked = true;
     }
     void* is = two ? (void*)aux->stream : stream;       // stream of the image-INR branch
+    // deferred zeroing needs the auxiliary streams; serial (instrumented) iterations zero inside Adam
+    const bool defer_zero = two && g_deferred_zero != 0;
+    if (zero_pending && !defer_zero) {      // the previous iteration deferred its zeroing, this one cannot
+      if (aux) cudaStreamWaitEvent(ms, aux->adam_i_done, 0);
+      cudaMemsetAsync(f->grads, 0, (size_t)(f->n_motion + f->n_image) * sizeof(float), ms);
+      zero_pending = false;
+    }
     if (ev) cudaEventRecord(ev[0], ms);
     // ---- forward -------------------------------------------------------------------------------
     K(0, is, immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is));
@@ -349,6 +366,15 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     K(7, is, immoco_grad_entropy(f->image, lambdas_host[it], loss + 1, f->d_image, 0, H, W, is));
     if (two) cudaEventRecord(aux->join_fwd, aux->stream);
     K(2, ms, M > 0 ? immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream) : nop());
+    if (defer_zero && zero_pending) {
+      // gradients of the previous iteration were consumed by both Adam launches (Adam_m precedes this point
+      // on `ms`, Adam_i is awaited through its event): zero them now, beside the SM-bound kernels that follow
+      cudaEventRecord(aux->zero_start, ms);
+      cudaStreamWaitEvent(aux->zero_stream, aux->zero_start, 0);
+      cudaStreamWaitEvent(aux->zero_stream, aux->adam_i_done, 0);
+      cudaMemsetAsync(f->grads, 0, (size_t)(f->n_motion + f->n_image) * sizeof(float), aux->zero_stream);
+      cudaEventRecord(aux->zero_done, aux->zero_stream);
+    }
     K(3, ms, M > 0 ? immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream) : nop());
     if (two) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
     if (fuse_rows) {      // slots 4 / 8 (static row passes) are folded into slots 5 / 9
@@ -367,6 +393,10 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
       K(9, ms, M > 0 ? immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
                                               f->d_image, f->d_disp, H, W, stream) : nop());
     }
+    if (defer_zero && zero_pending) {      // first accumulation into the gradients of this iteration
+      cudaStreamWaitEvent(ms, aux->zero_done, 0);
+      zero_pending = false;
+    }
     K(10, ms, M > 0 ? immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
                                      gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream) : nop());
     if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
@@ -375,10 +405,16 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
                              gi + (int64_t)wi * 32, P, wi, f->act_image, is));
     K(13, is, immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is));
     // ---- update (zero_grad fused), one launch per INR so each follows its own branch ---------------
+    // (the LAST iteration of the call zeroes inside Adam, so the gradients are clean when the call returns)
+    const int adam_zeroes = (defer_zero && it + 1 < it_end) ? 0 : 1;
     K(14, ms, M > 0 ? immoco_adam_step(pm, gm, f->exp_avg, f->exp_avg_sq, f->n_motion, f->lr, f->beta1, f->beta2,
-                                       f->eps, it + 1, 1, stream) : nop());
+                                       f->eps, it + 1, adam_zeroes, stream) : nop());
     K(15, is, immoco_adam_step(pi, gi, f->exp_avg + f->n_motion, f->exp_avg_sq + f->n_motion, f->n_image, f->lr,
-                               f->beta1, f->beta2, f->eps, it + 1, 1, is));
+                               f->beta1, f->beta2, f->eps, it + 1, adam_zeroes, is));
+    if (!adam_zeroes) {
+      cudaEventRecord(aux->adam_i_done, aux->stream);
+      zero_pending = true;
+    }
   }
   if (forked) {
     cudaEventRecord(aux->join_end, aux->stream);

@@ -202,34 +202,51 @@ __device__ __forceinline__ float pair_weight(const float (&frac)[D], float w0, i
   return w;
 }
 
+// IMMOCO_HG_FWD_PTS points per lane pair and item (the gathers of all of them are issued before the first
+// use: 4 x PTS rows in flight per thread)
+#ifndef IMMOCO_HG_FWD_PTS
+#define IMMOCO_HG_FWD_PTS 2      // B200, 3-D grid at C2: 1 -> 130 us, 2 -> 125 us, 4 -> 128 us (tools/hg_levels.py)
+#endif
+constexpr int kFwdPts = IMMOCO_HG_FWD_PTS;
+
 template <int D, int MODE>
 __device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, const float2* __restrict__ tab,
                                               float2* __restrict__ enc_level, int n, int base, float scale,
                                               uint32_t res, uint32_t entries, uint32_t hashed, uint32_t swz) {
   const int half = threadIdx.x & 1;
-  const int i = base + (threadIdx.x >> 1);
-  float2 acc = make_float2(0.f, 0.f);
-  if (i < n) {
-    uint32_t cell[D];
-    float frac[D];
+  constexpr int NC = 1 << (D - 1);
+  float2 v[kFwdPts][NC];
+  float frac[kFwdPts][D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+  for (int p = 0; p < kFwdPts; ++p) {
+    const int i = base + p * kPairPoints + (threadIdx.x >> 1);
+    uint32_t cell[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { cell[d] = 0; frac[p][d] = 0.f; }
+    if (i < n) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[p][d]);
+    }
     PairTerms<D, MODE> pt;
     pt.init(cell, half, entries, res, hashed, swz);
-    const float w0 = half ? frac[0] : 1.0f - frac[0];
-    float2 v[1 << (D - 1)];
 #pragma unroll
-    for (int c = 0; c < (1 << (D - 1)); ++c) v[c] = load_row(tab + pt.index(c));     // all gathers in flight
-#pragma unroll
-    for (int c = 0; c < (1 << (D - 1)); ++c) {
-      const float w = pair_weight<D>(frac, w0, c);
-      acc.x = fmaf(w, v[c].x, acc.x);
-      acc.y = fmaf(w, v[c].y, acc.y);
-    }
+    for (int c = 0; c < NC; ++c) v[p][c] = (i < n) ? load_row(tab + pt.index(c)) : make_float2(0.f, 0.f);   // all gathers in flight
   }
-  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
-  acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-  if (i < n && half == 0) enc_level[i] = acc;
+#pragma unroll
+  for (int p = 0; p < kFwdPts; ++p) {
+    const int i = base + p * kPairPoints + (threadIdx.x >> 1);
+    const float w0 = half ? frac[p][0] : 1.0f - frac[p][0];
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float w = pair_weight<D>(frac[p], w0, c);
+      acc.x = fmaf(w, v[p][c].x, acc.x);
+      acc.y = fmaf(w, v[p][c].y, acc.y);
+    }
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+    if (i < n && half == 0) enc_level[i] = acc;
+  }
 }
 
 template <int D>
@@ -242,7 +259,7 @@ hashgrid_fwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float
   // set at any time; with a capped grid (immoco_set_hashgrid_ctas_per_sm) the CTAs are persistent
   for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
     const int level = level0 + item / tiles;
-    const int base = (item % tiles) * kPairPoints;
+    const int base = (item % tiles) * (kPairPoints * kFwdPts);
     const float scale = g.scale[level];
     const uint32_t res = g.resolution[level];
     const uint32_t entries = g.entries[level];
@@ -257,46 +274,61 @@ hashgrid_fwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float
   }
 }
 
+#ifndef IMMOCO_HG_BWD_PTS
+#define IMMOCO_HG_BWD_PTS 1
+#endif
+constexpr int kBwdPts = IMMOCO_HG_BWD_PTS;
+
 template <int D, int MODE>
 __device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, const float2* __restrict__ d_enc_level,
                                               float2* __restrict__ gtab, int n, int base, float scale,
                                               uint32_t res, uint32_t entries, uint32_t swz) {
   const int half = threadIdx.x & 1;
-  const int i = base + (threadIdx.x >> 1);
-  float2 go = make_float2(0.f, 0.f);
-  uint32_t cell[D];
-  float frac[D];
+  float2 go[kBwdPts];
+  float x[kBwdPts][D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) { cell[d] = 0; frac[d] = 0.f; }
-  if (i < n) {
-    go = __ldg(d_enc_level + i);
+  for (int p = 0; p < kBwdPts; ++p) {          // all loads of the item before the first reduction
+    const int i = base + p * kPairPoints + (threadIdx.x >> 1);
+    go[p] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+    for (int d = 0; d < D; ++d) x[p][d] = 0.f;
+    if (i < n) {
+      go[p] = __ldg(d_enc_level + i);
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[p][d] = __ldg(coords + (size_t)i * D + d);
+    }
   }
-  const bool live = !(go.x == 0.0f && go.y == 0.0f);      // adding +-0 is a no-op (also covers i >= n)
-  PairTerms<D, MODE> pt;
-  pt.init(cell, half, entries, res, 1u, swz);
-  const float w0 = half ? frac[0] : 1.0f - frac[0];
-  // The two lanes' hash indices differ by X = cell ^ (cell + 1) (hash prime 1 on dimension 0); the row layout
-  // S is linear, so their rows differ by S(X).  S(X) == 1 (reference layout: even base cell): the rows are
-  // idx and idx ^ 1, one aligned 16-byte slot -> ONE 128-bit reduction (RED.ADD.F32x4) issued by the even
-  // lane instead of two 64-bit ones.  Both lanes of a pair hold the same point: the predicate is pair-uniform.
-  const bool merge = (MODE == kIdxHash) && (grid_swizzle((cell[0] ^ (cell[0] + 1u)) & (entries - 1u), swz) == 1u);
 #pragma unroll
-  for (int c = 0; c < (1 << (D - 1)); ++c) {
-    const float w = pair_weight<D>(frac, w0, c);
-    const uint32_t idx = pt.index(c);
-    const float vx = w * go.x, vy = w * go.y;
-    const float ox = __shfl_xor_sync(0xffffffffu, vx, 1);
-    const float oy = __shfl_xor_sync(0xffffffffu, vy, 1);
-    if (!live) continue;
-    if (merge) {
-      if (half == 0) {
-        const float4 v = (idx & 1u) ? make_float4(ox, oy, vx, vy) : make_float4(vx, vy, ox, oy);
-        atomicAdd(reinterpret_cast<float4*>(gtab + (idx & ~1u)), v);
+  for (int p = 0; p < kBwdPts; ++p) {
+    uint32_t cell[D];
+    float frac[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) grid_pos(x[p][d], scale, cell[d], frac[d]);
+    const bool live = !(go[p].x == 0.0f && go[p].y == 0.0f);      // adding +-0 is a no-op (also covers i >= n)
+    PairTerms<D, MODE> pt;
+    pt.init(cell, half, entries, res, 1u, swz);
+    const float w0 = half ? frac[0] : 1.0f - frac[0];
+    // The two lanes' hash indices differ by X = cell ^ (cell + 1) (hash prime 1 on dimension 0); the row layout
+    // S is linear, so their rows differ by S(X).  S(X) == 1 (reference layout: even base cell): the rows are
+    // idx and idx ^ 1, one aligned 16-byte slot -> ONE 128-bit reduction (RED.ADD.F32x4) issued by the even
+    // lane instead of two 64-bit ones.  Both lanes of a pair hold the same point: the predicate is pair-uniform.
+    const bool merge = (MODE == kIdxHash) && (grid_swizzle((cell[0] ^ (cell[0] + 1u)) & (entries - 1u), swz) == 1u);
+#pragma unroll
+    for (int c = 0; c < (1 << (D - 1)); ++c) {
+      const float w = pair_weight<D>(frac, w0, c);
+      const uint32_t idx = pt.index(c);
+      const float vx = w * go[p].x, vy = w * go[p].y;
+      const float ox = __shfl_xor_sync(0xffffffffu, vx, 1);
+      const float oy = __shfl_xor_sync(0xffffffffu, vy, 1);
+      if (!live) continue;
+      if (merge) {
+        if (half == 0) {
+          const float4 v = (idx & 1u) ? make_float4(ox, oy, vx, vy) : make_float4(vx, vy, ox, oy);
+          atomicAdd(reinterpret_cast<float4*>(gtab + (idx & ~1u)), v);
+        }
+      } else {
+        atomicAdd(gtab + idx, make_float2(vx, vy));
       }
-    } else {
-      atomicAdd(gtab + idx, make_float2(vx, vy));
     }
   }
 }
@@ -310,7 +342,7 @@ hashgrid_bwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float
   pdl_wait();
   for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
     const int level = level0 + item / tiles;
-    const int base = (item % tiles) * kPairPoints;
+    const int base = (item % tiles) * (kPairPoints * kBwdPts);
     const float scale = g.scale[level];
     const uint32_t res = g.resolution[level];
     const uint32_t entries = g.entries[level];
@@ -355,7 +387,7 @@ static int run_fwd(const immoco_grid_desc* grid, const float* coords, const floa
   const int n = (int)n_points;
   cudaStream_t s = (cudaStream_t)stream;
   if (g_pair) {
-    const int tiles = (int)ceil_div64(n, kPairPoints);
+    const int tiles = (int)ceil_div64(n, kPairPoints * kFwdPts);
     const int64_t items = (int64_t)tiles * (l1 - l0);
     const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
     const unsigned g = (unsigned)(items < cap ? items : cap);
@@ -393,7 +425,7 @@ static int run_bwd(const immoco_grid_desc* grid, const float* coords, const floa
       if (gx < g.x) g.x = gx;
     }
     if (pair) {
-      const int tiles = (int)ceil_div64(n, kPairPoints);
+      const int tiles = (int)ceil_div64(n, kPairPoints * kBwdPts);
       const int64_t items = (int64_t)tiles * (b - a);
       const int64_t cap = per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * per_sm : items;
       const unsigned gp = (unsigned)(items < cap ? items : cap);

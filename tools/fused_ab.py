@@ -23,9 +23,9 @@ for fused in (0, 1):
 rel = np.abs(traces[1] - traces[0]) / np.abs(traces[0])
 print("loss rel diff fused vs separate, its 0..11:", " ".join(f"{r:.1e}" for r in rel), flush=True)
 for rep in range(2):
-    for fused in (0, 1):
-        lib.immoco_set_fused_rows(fused)
+    for fused, dz in ((0, 0), (1, 0), (1, 1)):
+        lib.immoco_set_fused_rows(fused); lib.immoco_set_deferred_zero(dz)
         eng.reset(p_img, p_mot)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.run(lam, 1e-2, 0, 100); e0.record(); eng.run(lam, 1e-2, 100, 600); e1.record(); torch.cuda.synchronize()
-        print(f"fused={fused}: {e0.elapsed_time(e1)/500*1e3:.1f} us / iteration   final loss {eng.loss_trace(lam)[599]:.5f}", flush=True)
+        print(f"fused rows={fused} deferred zero={dz}: {e0.elapsed_time(e1)/500*1e3:.1f} us / iteration   final loss {eng.loss_trace(lam)[599]:.5f}", flush=True)
