@@ -97,7 +97,9 @@ int immoco_pdl_enabled() { return g_pdl; }
 // 1 (default): hot-path kernels are launched with programmatic stream serialization (common.cuh)
 extern "C" int immoco_set_pdl(int32_t on) { g_pdl = on ? 1 : 0; return 0; }
 
-static int g_adam_variant = 0, g_adam_ctas_per_sm = 32;
+// default: one 128-bit item per thread, streaming (evict-first) gradients / moments -- measured inside the iteration
+// (tools/adam_iter_ab.py): variant 0: 629.7, 3: 627.7, 1: 661, 4: 654, 2 / 5: 680+ us
+static int g_adam_variant = 3, g_adam_ctas_per_sm = 32;
 // tuning knobs (tools/adam_bench.py): variant = {U=1,2,4} x {plain, streaming hints}; CTAs per SM
 extern "C" int immoco_set_adam_tuning(int32_t variant, int32_t ctas_per_sm) {
   if (variant < 0 || variant > 5 || ctas_per_sm < 1 || ctas_per_sm > 64) return IMMOCO_ERR_BAD_ARG;
