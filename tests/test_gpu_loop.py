@@ -411,3 +411,42 @@ def test_engine_row_swizzle_equals_reference_layout():
     assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
     assert np.allclose(out[True][3], out[False][3], rtol=1e-4)
     assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < 1e-3
+
+
+def test_deferred_gradient_zeroing_equals_zeroing_in_adam():
+    """immoco_fit_run zeroes the gradients with one memset on a third stream (Adam leaves them in place).  The
+    loss trace must equal the run where Adam zeroes them itself -- a missed or late memset would accumulate
+    gradients and diverge within an iteration -- also when instrumented (serial) iterations, which cannot defer,
+    are interleaved with two-stream ones, and when the run is split into several calls."""
+    import ctypes as C
+    lib = mb.lib()
+    case = orc.make_case(64, 48, 2, 1000)
+    masks, k = case["masks"].to(DEV), case["kspace_motion"]
+    model = mb.IMMoCo(masks)
+    p_img = model.image_inr.params.detach().clone()
+    p_mot = model.motion_inr.params.detach().clone()
+    iters = 12
+    lam = mb.lambda_schedule(iters, 1e-2)
+    eng = mb.FitEngine(model, iters)
+    eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
+    traces = {}
+    try:
+        for name, defer, every, chunks in (("adam", 0, 0, [(0, iters)]), ("deferred", 1, 0, [(0, iters)]),
+                                           ("deferred+serial", 1, 3, [(0, iters)]),
+                                           ("deferred+chunks", 1, 0, [(0, 5), (5, 6), (6, iters)])):
+            lib.immoco_set_deferred_zero(defer)
+            eng.reset(p_img, p_mot)
+            prof = lib.immoco_profile_create(8) if every else None
+            for a, b in chunks:
+                eng.run(lam, 1e-2, a, b, profile=prof, profile_every=every)
+            torch.cuda.synchronize()
+            if prof:
+                lib.immoco_profile_destroy(prof)
+            traces[name] = eng.loss_trace(lam).copy()
+            assert float(eng.state[0].abs().max()) == 0.0, name      # gradients are clean when a call returns
+    finally:
+        lib.immoco_set_deferred_zero(1)
+    ref = traces["adam"]
+    for name, tr in traces.items():
+        rel = np.abs(tr - ref) / np.abs(ref)
+        assert rel[:4].max() < 1e-5 and rel.max() < 5e-3, (name, rel)
