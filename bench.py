@@ -124,16 +124,18 @@ def algorithmic_bytes(slot: str, p: int, m: int, n_par: int, t_img: int, t_mot: 
     return table[slot]
 
 
-# what actually paces each kernel (ncu --set full, profiles/round1_v5_ncu_full.txt)
+# what actually paces each kernel (ncu --set full, profiles/round1_v8_ncu_full.txt / round1_v9_ncu_full.txt)
 LIMITERS = {
-    "hashgrid_bwd_motion": "L2 atomic throughput (ncu lts 82 %, DRAM 9.5 %): 52.4 M 8-byte reductions on hashed rows "
-                           "with no locality across pixels; DRAM traffic equals the algorithmic bytes",
-    "hashgrid_fwd_motion": "L2 / L1TEX gather rate (ncu l1tex 79 %, lts 62 %, DRAM 9 %): 52.4 M 8-byte gathers on hashed rows",
-    "hashgrid_bwd_image": "L2 atomic throughput (ncu lts 51 %)", "hashgrid_fwd_image": "L2 / L1TEX gather rate",
-    "adam_motion": "HBM (ncu DRAM 69 % of its peak; 5.2 TB/s algorithmic)", "adam_image": "HBM",
-    "mlp_bwd_motion": "tcgen05 issue + SIMT epilogue (ncu sm 44 %, tensor pipe 20 %)",
-    "mlp_bwd_image": "tcgen05 issue + SIMT epilogue (ncu sm 33 %, tensor pipe 23 %)",
-    "mlp_fwd_motion": "SIMT epilogue (tanhf)", "mlp_fwd_image": "latency (2.7 tiles per CTA)",
+    "hashgrid_bwd_motion": "L1 wavefronts + L2 atomic throughput (ncu v9: l1tex 78 %, lts 74 %, DRAM 10 %): 52.4 M 8-byte "
+                           "reductions on hashed rows with no locality across pixels; DRAM traffic equals the algorithmic bytes",
+    "hashgrid_fwd_motion": "L1 wavefronts (ncu v9: l1tex 75 %, lts 57 %, DRAM 10 %): 52.4 M 8-byte gathers on hashed rows, "
+                           "one 128-byte line per lane pair",
+    "hashgrid_bwd_image": "L2 atomic throughput", "hashgrid_fwd_image": "L1 wavefronts / L2 gather rate",
+    "adam_motion": "HBM (28 B / parameter at ~5.9 TB/s; the zeroing of the gradients runs as a memset on a third stream)",
+    "adam_image": "HBM",
+    "mlp_bwd_motion": "barrier / MMA-chain latency + SIMT epilogue (ncu v8: issue active 36 %, tensor pipe 27 %)",
+    "mlp_bwd_image": "MMA-chain waits + SIMT epilogue (ncu v8: issue active 34 %, tensor pipe 27 %)",
+    "mlp_fwd_motion": "latency, 16 warps per SM (ncu v8: issue active 40 %)", "mlp_fwd_image": "latency (2.7 tiles per CTA)",
 }
 
 # SURVEY 8(d) / oracle.touched_entries(): distinct table rows touched at 320x320
