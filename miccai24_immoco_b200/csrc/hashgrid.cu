@@ -254,8 +254,14 @@ __device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, 
   }
 }
 
+// resident CTAs per SM the forward kernel is compiled for: 6 -> 40 registers with two points per lane pair
+// (5 CTAs at the unconstrained 44).  Iteration on B200: unconstrained 625 us, 6: 620.5, 7 / 8 (32 registers,
+// 24 bytes of spills): 619-622 (gpurun_out/r104)
+#ifndef IMMOCO_HG_FWD_MIN_CTAS
+#define IMMOCO_HG_FWD_MIN_CTAS 6
+#endif
 template <int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, IMMOCO_HG_FWD_MIN_CTAS)
 hashgrid_fwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
                          const float2* __restrict__ table, float2* __restrict__ enc, int n, int level0,
                          int n_levels, int tiles) {
