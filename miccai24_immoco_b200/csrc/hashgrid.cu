@@ -10,7 +10,11 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+// threads per CTA of every hash-grid kernel (iteration on B200: 128 -> 621 us, 256 -> 623 us, 512 -> 648 us)
+#ifndef IMMOCO_HG_THREADS
+#define IMMOCO_HG_THREADS 256
+#endif
+constexpr int kThreads = IMMOCO_HG_THREADS;
 
 // table-row gather of the forward kernels.  Rows are re-used ~6x per pass but by unrelated pixels, so L1
 // never hits beyond the lane pair itself: IMMOCO_HG_LOAD selects the cache policy of the gather
@@ -258,7 +262,7 @@ __device__ __forceinline__ void fwd_pair_item(const float* __restrict__ coords, 
 // (5 CTAs at the unconstrained 44).  Iteration on B200: unconstrained 625 us, 6: 620.5, 7 / 8 (32 registers,
 // 24 bytes of spills): 619-622 (gpurun_out/r104)
 #ifndef IMMOCO_HG_FWD_MIN_CTAS
-#define IMMOCO_HG_FWD_MIN_CTAS 6
+#define IMMOCO_HG_FWD_MIN_CTAS (1536 / IMMOCO_HG_THREADS)
 #endif
 template <int D>
 __global__ void __launch_bounds__(kThreads, IMMOCO_HG_FWD_MIN_CTAS)
