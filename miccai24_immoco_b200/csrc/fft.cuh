@@ -47,13 +47,20 @@ __host__ __device__ __forceinline__ float2 fft_cmul(float2 a, float2 b) {
 }
 
 // One radix-R butterfly `j` (0 <= j < N/R) of the Stockham stage with sub-transform size Ns.
+// a / d for 0 <= a < 2^20, 0 < d <= 2^12 without the integer-division routine: (a + 0.5) / d is at least
+// 0.5 / d away from an integer, far more than the rounding of the fp32 product (inv_d = 1.0f / d)
+__host__ __device__ __forceinline__ int fft_div(int a, float inv_d) {
+  return (int)(((float)a + 0.5f) * inv_d);
+}
+
+// Stage constants (uniform over the block): T = N / R butterflies per transform, twstep = N / (Ns R)
 template <bool INV>
 __host__ __device__ __forceinline__ void fft_butterfly(const float2* in, float2* out, int N, int R,
-                                                       int Ns, int j, const float2* tw) {
-  const int T = N / R;
-  const int k = j % Ns;
-  const int j0 = (j / Ns) * Ns * R + k;
-  const int twstep = N / (Ns * R);
+                                                       int Ns, int j, const float2* tw, int T, int twstep,
+                                                       float inv_ns) {
+  const int q = fft_div(j, inv_ns);
+  const int k = j - q * Ns;
+  const int j0 = q * Ns * R + k;
   if (R == 4) {
     float2 v0 = in[j];
     float2 v1 = fft_cmul(in[j + T], fft_tw<INV>(tw, k * twstep));
@@ -105,11 +112,13 @@ __device__ float2* fft_smem(float2* a, float2* b, int nfft, int tstride, const F
   int Ns = 1;
   for (int s = 0; s < plan.n_stages; ++s) {
     const int R = plan.radix[s];
-    const int T = N / R;
+    const int T = N / R;                       // uniform per stage: three divisions per stage, not per butterfly
+    const int twstep = N / (Ns * R);
+    const float inv_t = 1.0f / (float)T, inv_ns = 1.0f / (float)Ns;
     for (int idx = threadIdx.x; idx < nfft * T; idx += blockDim.x) {
-      const int t = idx / T;
+      const int t = fft_div(idx, inv_t);
       const int j = idx - t * T;
-      fft_butterfly<INV>(a + t * tstride, b + t * tstride, N, R, Ns, j, tw);
+      fft_butterfly<INV>(a + t * tstride, b + t * tstride, N, R, Ns, j, tw, T, twstep, inv_ns);
     }
     __syncthreads();
     float2* tmp = a; a = b; b = tmp;

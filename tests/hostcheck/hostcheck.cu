@@ -22,9 +22,11 @@ extern "C" int hostcheck_fft(const float* in, float* out, int n, int nfft, int i
     int Ns = 1;
     for (int s = 0; s < plan.n_stages; ++s) {
       const int R = plan.radix[s];
+      const int T = n / R, twstep = n / (Ns * R);
+      const float inv_ns = 1.0f / (float)Ns;
       for (int j = 0; j < n / R; ++j) {
-        if (inverse) fft_butterfly<true>(pa, pb, n, R, Ns, j, tw.data());
-        else fft_butterfly<false>(pa, pb, n, R, Ns, j, tw.data());
+        if (inverse) fft_butterfly<true>(pa, pb, n, R, Ns, j, tw.data(), T, twstep, inv_ns);
+        else fft_butterfly<false>(pa, pb, n, R, Ns, j, tw.data(), T, twstep, inv_ns);
       }
       std::swap(pa, pb);
       Ns *= R;
