@@ -157,18 +157,35 @@ colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ 
       if (c < nc) zero_after_load[(size_t)i * W + l0 + c] = make_float2(0.f, 0.f);
     }
   }
+  // the measured k-space of this CTA's columns: requested now, consumed after the forward transform
+  constexpr int kMaxPre = 4;                       // items per thread held in registers (H * CPC <= 1024)
+  float2 kin_pre[kMaxPre];
+#pragma unroll
+  for (int u = 0; u < kMaxPre; ++u) {
+    const int idx = threadIdx.x + u * kThreads;
+    const int k = idx / CPC, c = idx - k * CPC;
+    kin_pre[u] = (idx < H * CPC && c < nc) ? __ldg(k_in + (size_t)k * W + l0 + c) : make_float2(0.f, 0.f);
+  }
   __syncthreads();
   float2* res = fft_smem<false>(a, b, nc, HP, plan, tw);
   float2* other = (res == a) ? b : a;
   const float inv_hw = 1.0f / ((float)H * (float)W);
   float part = 0.0f;
-  for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads) {
+  int u_it = 0;
+  for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads, ++u_it) {
     const int k = idx / CPC, c = idx - k * CPC;
     if (c < nc) {
       int kk = k + half; if (kk >= H) kk -= H;
       const float2 v = res[c * HP + kk];
       const size_t g = (size_t)k * W + l0 + c;
-      const float2 t = __ldg(k_in + g);
+      float2 t;
+      if (u_it < kMaxPre) {
+        t = kin_pre[0];
+#pragma unroll
+        for (int u = 1; u < kMaxPre; ++u) if (u == u_it) t = kin_pre[u];
+      } else {
+        t = __ldg(k_in + g);
+      }
       k_out[g] = v;
       const float dx = v.x - t.x, dy = v.y - t.y;
       part = fmaf(dx, dx, part);
@@ -322,6 +339,9 @@ __device__ __forceinline__ void motion_rows_bwd_body(const float2* __restrict__ 
   const float inv_w = 1.0f / (float)W;
   for (int j = threadIdx.x; j < W; j += kThreads) {
     const int bq = j - half;
+    // requested before the pruned DFT so that the round trip hides behind it
+    const float2 d = __ldg(disp + base + j);
+    const float2 id = __ldg(ident + (size_t)i * W + j);
     float gr = 0.f, gi = 0.f;   // cotangent of the moved pixel (re, im)
     for (int li = 0; li < nl; ++li) {
       const float2 w = tw[wrap_mod_fast(la[li] * bq, W, inv_w)];
@@ -329,8 +349,6 @@ __device__ __forceinline__ void motion_rows_bwd_body(const float2* __restrict__ 
       gr += g.x * w.x + g.y * w.y;     // g * conj(w)
       gi += g.y * w.x - g.x * w.y;
     }
-    const float2 d = __ldg(disp + base + j);
-    const float2 id = __ldg(ident + (size_t)i * W + j);
     const Taps t = make_taps(id.x + d.x, id.y + d.y, H, W);
     const int x0 = t.x0, y0 = t.y0, x1 = t.x0 + 1, y1 = t.y0 + 1;
     const bool inx0 = (unsigned)x0 < (unsigned)W, inx1 = (unsigned)x1 < (unsigned)W;
