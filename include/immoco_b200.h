@@ -8,7 +8,8 @@
  *
  * Conventions
  *  - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
- *    (the torch caching allocator in the shipped host code); the library allocates nothing;
+ *    (the torch caching allocator in the shipped host code); the library allocates no device memory
+ *    (its only hidden state: one auxiliary stream set per caller stream, immoco_release_streams());
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises;
  *  - return value: 0 on success, otherwise the cudaError_t of the failed launch, or
  *    IMMOCO_ERR_* (negative) for rejected arguments;
@@ -90,6 +91,37 @@ int immoco_set_hashgrid_ctas_per_sm(int32_t ctas);
  * and registers to an SM-bound kernel of the other INR branch. */
 int immoco_set_hashgrid_bwd_ctas_per_sm(int32_t ctas);
 
+/* ---- (1b) deterministic hash-grid backward: the coordinates of an IM-MoCo fit are constant
+ *          (src/models/immoco.py:72-80 registers them as buffers), so the scatter of
+ *          kernel_grid_backward can be turned around ONCE per coordinate set into a row-sorted tap list
+ *          (CSR): the taps of physical table row r are taps[row_ptr[r] .. row_ptr[r+1]), each tap = 8 bytes
+ *          {uint32 point index, float interpolation weight}, ordered by (point, corner).  The backward
+ *          pass is then a gather with a FIXED summation order per row: bit-reproducible, no atomics, and
+ *          rows that no point touches are never written.  All arrays are caller-owned device memory. ---- */
+typedef struct immoco_grid_csr {
+  const uint32_t* row_ptr;   /* n_rows + 1 entries (n_rows = grid->offset[n_levels])                */
+  const void* taps;          /* n_taps x {uint32 point, float weight}                               */
+  int64_t n_taps;            /* n_points * 2^n_dims * n_levels                                      */
+  int64_t n_points;
+} immoco_grid_csr;
+/* bytes of scratch immoco_hashgrid_csr_build needs (sort keys of one level, double-buffered, + radix-sort
+ * temporaries); < 0: invalid arguments */
+int64_t immoco_hashgrid_csr_workspace_bytes(const immoco_grid_desc* grid, int64_t n_points);
+/* builds row_ptr (n_rows + 1 uint32) and taps (n_taps x 8 bytes) for `coords` ((n_points, n_dims) fp32) */
+int immoco_hashgrid_csr_build(const immoco_grid_desc* grid, const float* coords, int64_t n_points,
+                              uint32_t* row_ptr, void* taps, void* workspace, int64_t workspace_bytes,
+                              void* stream);
+/* grad_table[r] = sum_k taps[k].weight * d_enc[level(r)][taps[k].point] for every touched row r (WRITTEN, not
+ * accumulated; untouched rows are left alone).  Same values as immoco_hashgrid_bwd up to summation order. */
+int immoco_hashgrid_bwd_csr(const immoco_grid_desc* grid, const immoco_grid_csr* csr, const float* d_enc,
+                            float* grad_table, void* stream);
+/* the same gather with torch.optim.Adam fused in: the thread that owns row r applies the update to
+ * params / exp_avg / exp_avg_sq of that row at once (rows nobody touches have g = m = v = 0 for ever and
+ * never move under dense Adam either, src/models/immoco.py:149-154).  grad_table may be NULL. */
+int immoco_hashgrid_bwd_csr_adam(const immoco_grid_desc* grid, const immoco_grid_csr* csr, const float* d_enc,
+                                 float* table, float* exp_avg, float* exp_avg_sq, float* grad_table, double lr,
+                                 double beta1, double beta2, double eps, int32_t step, void* stream);
+
 /* ---- (2) INR MLP: replaces the network half of tcnn.NetworkWithInputEncoding
  *          (configs at src/models/immoco.py:11-25).  One hidden layer of `width` (64 or 256),
  *          no biases, W1: width x 32, W2: 16 x width (rows >= 2 are padding).
@@ -100,10 +132,19 @@ int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2, float* ou
 int immoco_mlp_bwd(const float* enc, const float* w1, const float* w2, const float* d_out,
                    float* d_enc, float* g_w1, float* g_w2, int64_t n_points, int32_t width,
                    int32_t act, void* stream);
-/* MLP kernel selection for A/B checks: 0 = fp32 SIMT kernels, 1 = tcgen05 (kind::tf32, 3xTF32
- * split, accumulators in TMEM).  Both satisfy the same fp32-parity tolerances. */
-int immoco_set_mlp_impl(int32_t impl);
-int immoco_get_mlp_impl(void);
+/* Deterministic weight gradients: every CTA of the tensor-core backward kernel writes ITS partial
+ * [g_W1 | g_W2] (same layout as the MLP parameters, width*32 + 16*width floats) to
+ * g_part[cta * n_mlp ..]; the CTA -> tile assignment is static, so the partials are reproducible and
+ * the consumer (immoco_adam_step_partials) adds them in CTA order.  g_part must hold
+ * immoco_mlp_bwd_partial_count(n_points) blocks and be ZERO outside the rows the kernel writes (the 14
+ * padding rows of W2).  Tensor-core implementation only. */
+int immoco_mlp_bwd_partials(const float* enc, const float* w1, const float* w2, const float* d_out,
+                            float* d_enc, float* g_part, int64_t n_points, int32_t width, int32_t act,
+                            void* stream);
+int immoco_mlp_bwd_partial_count(int64_t n_points);
+/* (The fp32 SIMT A/B kernels of round 1 are no longer part of this library: they are built into the
+ * test-side checker tests/checkers/_mlp_simt.so.  The product MLPs are tcgen05 kind::tf32, 3xTF32 split,
+ * accumulators in TMEM.) */
 /* element-wise helper for the autograd wrapper: d_pre = d_post * (1 - y^2) */
 int immoco_tanh_bwd(const float* y, const float* d_post, float* d_pre, int64_t n, void* stream);
 
@@ -142,6 +183,11 @@ int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc, 
 int immoco_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                      double lr, double beta1, double beta2, double eps, int32_t step,
                      int32_t zero_grad, void* stream);
+/* Adam over the first n_mlp parameters with the gradient taken as sum_{c < n_part} g_part[c * n_mlp + i]
+ * (added in CTA order: deterministic); params / moments point at the INR's MLP block. */
+int immoco_adam_step_partials(float* params, const float* g_part, int32_t n_part, float* exp_avg,
+                              float* exp_avg_sq, int64_t n_mlp, double lr, double beta1, double beta2,
+                              double eps, int32_t step, void* stream);
 /* tuning knobs of the Adam kernel (tools/adam_bench.py): variant 0..5 = {1,2,4 items per thread} x
  * {plain, streaming cache hints}; resident 256-thread CTAs per SM. Results are identical. */
 int immoco_set_adam_tuning(int32_t variant, int32_t ctas_per_sm);
@@ -169,7 +215,35 @@ typedef struct immoco_fit {
   float* c_tmp; float* d_c; float* k_out;   /* P x 2 each                                    */
   double* loss;                    /* 2 doubles per iteration: sum|dK|^2, GE (pre-zeroed)    */
   double lr, beta1, beta2, eps;
+  /* ---- reproducible accumulation (all optional; NULL / 0 = the float-atomic path) ----------------------
+   * loss_slots: per-iteration, per-CTA partial sums of the two loss terms, slots_per_iter =
+   *   immoco_fit_loss_slots() doubles per iteration; immoco_fit_run adds them in slot order into `loss` at
+   *   the end of the call (no floating-point atomics on the loss).
+   * deterministic != 0 additionally requires every buffer below and makes two runs of the same call
+   * bit-identical: hash-grid backward = row-sorted gather (csr_*), MLP weight gradients = per-CTA partials
+   * added in CTA order (mlp_part_*), image cotangent accumulated in 64-bit fixed point (d_image_fx, scaled
+   * per iteration by the largest column-pass cotangent, dc_max_bits[it]).  fuse_adam != 0: the table rows
+   * are updated inside the gather kernel (no gradient round trip through HBM). */
+  double* loss_slots;
+  int32_t deterministic;
+  int32_t fuse_adam;
+  immoco_grid_csr csr_image;
+  immoco_grid_csr csr_motion;
+  float* mlp_part_image;           /* immoco_mlp_bwd_partial_count(P)   x n_mlp_image floats, zeroed */
+  float* mlp_part_motion;          /* immoco_mlp_bwd_partial_count(M*P) x n_mlp_motion floats, zeroed */
+  int64_t* d_image_fx;             /* 2*P int64, zeroed by the caller once                    */
+  uint32_t* dc_max_bits;           /* one word per iteration, zeroed by the caller            */
 } immoco_fit;
+/* doubles per iteration of immoco_fit::loss_slots for an (h, w) slice: out[0] column-pass CTAs (data
+ * consistency), out[1] gradient-entropy CTAs; slots_per_iter = out[0] + out[1] */
+int immoco_fit_loss_slots(int32_t h, int32_t w, int32_t out[2]);
+/* process-wide default consulted by the shipped host code when it builds a fit (the C ABI itself takes the
+ * mode per call through immoco_fit::deterministic): 1 = bit-reproducible fits. */
+int immoco_set_deterministic(int32_t on);
+int immoco_get_deterministic(void);
+/* destroys the auxiliary streams / events immoco_fit_run created for caller streams of the current device
+ * (the library's only hidden state); safe to call when no fit is in flight.  Returns the number freed. */
+int immoco_release_streams(void);
 
 /* Optional per-kernel timing: events are recorded around every kernel of each iteration `it`
  * with it % profile_every == profile_every - 1 (prof may be NULL).  Slot order:
@@ -248,10 +322,12 @@ int immoco_rigid_bicubic_bwd_theta(const float* images, const float* theta, cons
 
 /* library/ABI version and the number of kernel launches one fit iteration issues */
 int immoco_abi_version(void);
-/* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit): lets a foreign-language
- * binding assert that its struct mirrors match this build. */
-void immoco_struct_sizes(int32_t out[3]);
+/* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit), sizeof(immoco_grid_csr): lets a
+ * foreign-language binding assert that its struct mirrors match this build. */
+void immoco_struct_sizes(int32_t out[4]);
 int immoco_launches_per_iteration(int32_t m);
+/* the same for a fit with immoco_fit::deterministic / fuse_adam set */
+int immoco_launches_per_iteration_mode(int32_t m, int32_t deterministic, int32_t fuse_adam);
 /* 1 (default): immoco_fit_run issues the static row pass and the pruned motion rows of an iteration as ONE
  * launch forward and ONE launch for the adjoint (16 launches per iteration); 0: four separate launches
  * (18 per iteration; A/B check -- results agree to rounding). */

@@ -14,7 +14,8 @@ _ROOT = os.path.dirname(_HERE)
 # IMMOCO_LIB_PATH / IMMOCO_NVCC_FLAGS: build-variant experiments (tools/), not used by the product path
 LIB_PATH = os.environ.get("IMMOCO_LIB_PATH") or os.path.join(_HERE, "libimmoco_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["hashgrid.cu", "mlp.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu", "unet.cu", "autofocus.cu"]
+SOURCES = ["hashgrid.cu", "hashgrid_csr.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu", "unet.cu",
+           "autofocus.cu"]
 
 MAX_LEVELS = 16
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -35,6 +36,15 @@ class GridDesc(C.Structure):
         ("offset", C.c_uint32 * (MAX_LEVELS + 1)),
         ("hashed", C.c_uint32 * MAX_LEVELS),
         ("swizzle", C.c_uint32 * MAX_LEVELS),
+    ]
+
+
+class GridCsr(C.Structure):
+    _fields_ = [
+        ("row_ptr", C.c_void_p),
+        ("taps", C.c_void_p),
+        ("n_taps", C.c_int64),
+        ("n_points", C.c_int64),
     ]
 
 
@@ -69,6 +79,11 @@ class Fit(C.Structure):
         ("c_tmp", C.c_void_p), ("d_c", C.c_void_p), ("k_out", C.c_void_p),
         ("loss", C.c_void_p),
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("loss_slots", C.c_void_p),
+        ("deterministic", C.c_int32), ("fuse_adam", C.c_int32),
+        ("csr_image", GridCsr), ("csr_motion", GridCsr),
+        ("mlp_part_image", C.c_void_p), ("mlp_part_motion", C.c_void_p),
+        ("d_image_fx", C.c_void_p), ("dc_max_bits", C.c_void_p),
     ]
 
 
@@ -81,12 +96,24 @@ _SIGNATURES = {
     "immoco_mlp_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "immoco_tanh_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
-    "immoco_set_mlp_impl": (C.c_int, [C.c_int32]),
+    "immoco_hashgrid_csr_workspace_bytes": (C.c_int64, [C.POINTER(GridDesc), C.c_int64]),
+    "immoco_hashgrid_csr_build": (C.c_int, [C.POINTER(GridDesc), _P, C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "immoco_hashgrid_bwd_csr": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P]),
+    "immoco_hashgrid_bwd_csr_adam": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P, _P, _P, C.c_double,
+                                               C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
+    "immoco_mlp_bwd_partials": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "immoco_mlp_bwd_partial_count": (C.c_int, [C.c_int64]),
+    "immoco_adam_step_partials": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_int32, _P]),
+    "immoco_fit_loss_slots": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "immoco_set_deterministic": (C.c_int, [C.c_int32]),
+    "immoco_get_deterministic": (C.c_int, []),
+    "immoco_release_streams": (C.c_int, []),
+    "immoco_launches_per_iteration_mode": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "immoco_set_hashgrid_impl": (C.c_int, [C.c_int32]),
     "immoco_set_hashgrid_ctas_per_sm": (C.c_int, [C.c_int32]),
     "immoco_set_hashgrid_bwd_ctas_per_sm": (C.c_int, [C.c_int32]),
     "immoco_set_adam_tuning": (C.c_int, [C.c_int32, C.c_int32]),
-    "immoco_get_mlp_impl": (C.c_int, []),
     "immoco_fft2c": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32,
                                C.c_float, _P]),
     "immoco_forward_model": (C.c_int, [_P, _P, _P, C.POINTER(Lines), _P, _P, _P, _P, C.c_int32,
@@ -166,9 +193,9 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)     # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        sizes = (C.c_int32 * 3)()
+        sizes = (C.c_int32 * 4)()
         handle.immoco_struct_sizes(sizes)
-        want = (C.sizeof(GridDesc), C.sizeof(Lines), C.sizeof(Fit))
+        want = (C.sizeof(GridDesc), C.sizeof(Lines), C.sizeof(Fit), C.sizeof(GridCsr))
         if tuple(sizes) != want:
             raise RuntimeError(f"struct layout mismatch: library {tuple(sizes)} vs binding {want}")
         _lib = handle

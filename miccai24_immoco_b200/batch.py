@@ -51,7 +51,8 @@ def reconstruct_batch(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Ten
                       image_params: Optional[Sequence[torch.Tensor]] = None,
                       motion_params: Optional[Sequence[torch.Tensor]] = None,
                       seeds: Optional[Sequence[int]] = None, kmax: float = 16000.0, variant: str = "main",
-                      return_kspace: bool = False, return_traces: bool = False, device=None):
+                      return_kspace: bool = False, return_traces: bool = False, device=None,
+                      deterministic: Optional[bool] = None):
     """``imcoco_motion_correction`` over a stack of slices, ``in_flight`` of them concurrently.
 
     kspaces[i]: (H, W) complex k-space, masks[i]: (M_i, H, W) movement-group masks (host or device;
@@ -91,7 +92,7 @@ def reconstruct_batch(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Ten
                 model.motion_inr.params.copy_(motion_params[i].to(dev, non_blocking=True))
         k_dev = _as_pinned(k_in).to(dev, non_blocking=True).to(torch.complex64)
         scale = k_dev.abs().max()                      # stays on the device (immoco.py:137-139)
-        engine = FitEngine(model, max(iters, 1))
+        engine = FitEngine(model, max(iters, 1), deterministic=deterministic)
         engine.set_kspace(k_dev.div(scale).mul(kmax))
         slot.index, slot.done, slot.model, slot.engine = i, 0, model, engine
 

@@ -5,7 +5,10 @@
 
 #include "immoco_b200.h"
 
-#define IMMOCO_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized as multiples of this
+// SM count of the CURRENT device (B200: 148 = 2 dies x 74), queried once per device (fit.cu); grids are
+// sized as multiples of it
+int immoco_num_sms();
+#define IMMOCO_NUM_SMS (immoco_num_sms())
 
 #define IMMOCO_LAUNCH_CHECK()                      \
   do {                                             \
@@ -25,6 +28,19 @@
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 int immoco_pdl_enabled();   // fit.cu
+
+// "first call on this device?" -- function attributes (dynamic shared-memory opt-in) are per device, so a
+// launcher keeps one of these as a function-local static instead of a process-wide flag
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 
 template <typename... P, typename... A>
 inline cudaError_t immoco_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -89,6 +105,26 @@ __host__ __device__ __forceinline__ void grid_pos(float x, float scale, uint32_t
   frac = pos - fl;
   cell = (uint32_t)(int)fl;
 }
+
+// ---------------------------------------------------------------------------------------------
+// torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False), single-tensor formulation
+// (src/models/immoco.py:149-154):  m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;
+// p -= step_size * m / (sqrt(v)/bc2_sqrt + eps).  ONE definition, explicit roundings, so the stand-alone
+// Adam kernels and the update fused into the hash-grid gather produce the same bits.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float omb1, float b2, float omb2,
+                                            float step_size, float bc2_sqrt, float eps) {
+  m = __fmaf_rn(omb1, __fsub_rn(g, m), m);
+  v = __fmaf_rn(__fmul_rn(omb2, g), g, __fmul_rn(b2, v));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+  p = __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);
+}
+
+// bias corrections in double like torch (python floats), then rounded to fp32 scalars
+struct AdamScalars {
+  float omb1, b2, omb2, step_size, bc2_sqrt, eps;
+};
+AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, int step);   // fit.cu
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);

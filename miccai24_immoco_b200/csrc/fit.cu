@@ -19,19 +19,23 @@ int immoco_rows_fwd_fused(const float* image, const float* disp, const float* id
                           const float* tw_w, float* c_out, int h, int w, void* stream);
 int immoco_rows_bwd_fused(const float* d_c, const float* image, const float* disp, const float* ident,
                           const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp, int h, int w,
-                          void* stream);
+                          int64_t* fx, const uint32_t* dmax_bits, void* stream);
 int immoco_colpass_loss_zero(float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
-                             const float* tw_h, int h, int w, void* stream);
+                             const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream);
+int immoco_colpass_loss_slots(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
+                              const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream);
+int immoco_grad_entropy_slots(const float* image, float grad_scale, double* loss_acc, float* d_image,
+                              int accumulate, int h, int w, double* loss_slots, void* stream);
+int immoco_d_image_finalize(float* d_image, int64_t* fx, const uint32_t* dmax_bits, int h, int w, void* stream);
+// mlp_tc.cu
+int immoco_mlp_bwd_tc_grid(int64_t n_points);
 
 namespace {
 
 // torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False), single-tensor formulation:
 //   m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
 // One pass: reads p,g,m,v, writes p,m,v and zeroes g (28 B / parameter), 128-bit accesses.
-#define IMMOCO_ADAM_LANE(c)                                              \
-  mi.c = mi.c + one_minus_b1 * (gi.c - mi.c);                            \
-  vi.c = fmaf(one_minus_b2 * gi.c, gi.c, b2 * vi.c);                     \
-  pi.c = pi.c - step_size * (mi.c / (sqrtf(vi.c) / bc2_sqrt + eps));
+#define IMMOCO_ADAM_LANE(c) adam_update(pi.c, mi.c, vi.c, gi.c, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
 
 // U independent 128-bit items per thread per trip: all 4*U loads are issued before the first use so
 // 64*U bytes per thread are in flight.  HINTS: gradients and moments are touched once per iteration
@@ -73,7 +77,6 @@ adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__
     }
   }
 }
-#undef IMMOCO_ADAM_LANE
 
 __global__ void adam_tail_kernel(float* p, float* g, float* m, float* v, int64_t begin, int64_t n,
                                  float one_minus_b1, float b2, float one_minus_b2, float step_size,
@@ -82,15 +85,86 @@ __global__ void adam_tail_kernel(float* p, float* g, float* m, float* v, int64_t
   const int64_t i = begin + threadIdx.x;
   if (i < n) {
     const float gi = g[i];
-    const float mi = m[i] + one_minus_b1 * (gi - m[i]);
-    const float vi = fmaf(one_minus_b2 * gi, gi, b2 * v[i]);
-    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-    m[i] = mi; v[i] = vi;
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, gi, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
+    p[i] = pi; m[i] = mi; v[i] = vi;
     if (zero_grad) g[i] = 0.f;
   }
 }
 
+// Adam over an INR's MLP block with the gradient assembled from the backward kernel's per-CTA partial blocks,
+// added in CTA order (deterministic mode).  The blocks are tiny (<= 148 x 48 KB) and L2-resident.
+__global__ void __launch_bounds__(256)
+adam_partials_kernel(float4* __restrict__ p, const float4* __restrict__ part, int n_part, float4* __restrict__ m,
+                     float4* __restrict__ v, int n4, float one_minus_b1, float b2, float one_minus_b2,
+                     float step_size, float bc2_sqrt, float eps) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 gi = make_float4(0.f, 0.f, 0.f, 0.f);
+  int c = 0;
+  for (; c + 4 <= n_part; c += 4) {          // four loads in flight, added in CTA order
+    const float4 a0 = __ldg(part + (size_t)c * n4 + i), a1 = __ldg(part + (size_t)(c + 1) * n4 + i);
+    const float4 a2 = __ldg(part + (size_t)(c + 2) * n4 + i), a3 = __ldg(part + (size_t)(c + 3) * n4 + i);
+    gi.x = ((((gi.x + a0.x) + a1.x) + a2.x) + a3.x);
+    gi.y = ((((gi.y + a0.y) + a1.y) + a2.y) + a3.y);
+    gi.z = ((((gi.z + a0.z) + a1.z) + a2.z) + a3.z);
+    gi.w = ((((gi.w + a0.w) + a1.w) + a2.w) + a3.w);
+  }
+  for (; c < n_part; ++c) {
+    const float4 a = __ldg(part + (size_t)c * n4 + i);
+    gi.x += a.x; gi.y += a.y; gi.z += a.z; gi.w += a.w;
+  }
+  float4 mi = m[i], vi = v[i], pi = p[i];
+  IMMOCO_ADAM_LANE(x) IMMOCO_ADAM_LANE(y) IMMOCO_ADAM_LANE(z) IMMOCO_ADAM_LANE(w)
+  m[i] = mi; v[i] = vi; p[i] = pi;
+}
+
+// loss[it] = sum of the iteration's per-CTA slots, added in slot order (immoco_fit::loss_slots)
+__global__ void loss_reduce_kernel(const double* __restrict__ slots, int per_iter, int n_dc, double* __restrict__ loss,
+                                   int it_begin, int it_end) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int it = it_begin + (t >> 1), which = t & 1;
+  if (it >= it_end) return;
+  const double* s = slots + (size_t)it * per_iter + (which ? n_dc : 0);
+  const int n = which ? per_iter - n_dc : n_dc;
+  double acc = 0.0;
+  for (int k = 0; k < n; ++k) acc += s[k];
+  loss[2 * (size_t)it + which] = acc;
+}
+
 }  // namespace
+#undef IMMOCO_ADAM_LANE
+
+// SM count of the current device, cached per device
+int immoco_num_sms() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    cache[dev] = sms;
+  }
+  return cache[dev];
+}
+
+AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, int step) {
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars a;
+  a.step_size = (float)(lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  a.omb1 = (float)(1.0 - beta1);
+  a.omb2 = (float)(1.0 - beta2);
+  a.b2 = (float)beta2;
+  a.eps = (float)eps;
+  return a;
+}
+
+static int g_deterministic = 0;
+extern "C" int immoco_set_deterministic(int32_t on) { g_deterministic = on ? 1 : 0; return 0; }
+extern "C" int immoco_get_deterministic(void) { return g_deterministic; }
 
 static int g_pdl = 1;
 int immoco_pdl_enabled() { return g_pdl; }
@@ -115,13 +189,8 @@ extern "C" int immoco_adam_step(float* params, float* grads, float* exp_avg, flo
   if (n == 0) return 0;
   if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0)
     return IMMOCO_ERR_BAD_ARG;
-  // bias corrections in double like torch (python floats), then rounded to fp32 scalars
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
-  const float step_size = (float)(lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
-  const float omb1 = (float)(1.0 - beta1);
-  const float omb2 = (float)(1.0 - beta2);
+  const AdamScalars sc = adam_scalars(lr, beta1, beta2, eps, step);
+  const float step_size = sc.step_size, bc2_sqrt = sc.bc2_sqrt, omb1 = sc.omb1, omb2 = sc.omb2;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n4 = n / 4;
   if (n4 > 0) {
@@ -151,18 +220,43 @@ extern "C" int immoco_adam_step(float* params, float* grads, float* exp_avg, flo
   return 0;
 }
 
-extern "C" int immoco_abi_version(void) { return 1; }
+extern "C" int immoco_adam_step_partials(float* params, const float* g_part, int32_t n_part, float* exp_avg,
+                                         float* exp_avg_sq, int64_t n_mlp, double lr, double beta1, double beta2,
+                                         double eps, int32_t step, void* stream) {
+  if (n_mlp < 0 || (n_mlp & 3) != 0 || n_part < 0 || step < 1 || n_mlp > 0x7fffffff) return IMMOCO_ERR_BAD_ARG;
+  if (n_mlp == 0) return 0;
+  if ((((uintptr_t)params | (uintptr_t)g_part | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0)
+    return IMMOCO_ERR_BAD_ARG;
+  const AdamScalars sc = adam_scalars(lr, beta1, beta2, eps, step);
+  const int n4 = (int)(n_mlp / 4);
+  immoco_launch(adam_partials_kernel, dim3((n4 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (float4*)params,
+                (const float4*)g_part, (int)n_part, (float4*)exp_avg, (float4*)exp_avg_sq, n4, sc.omb1, sc.b2, sc.omb2,
+                sc.step_size, sc.bc2_sqrt, sc.eps);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
 
-extern "C" void immoco_struct_sizes(int32_t out[3]) {
+extern "C" int immoco_abi_version(void) { return 2; }
+
+extern "C" void immoco_struct_sizes(int32_t out[4]) {
   out[0] = (int32_t)sizeof(immoco_grid_desc);
   out[1] = (int32_t)sizeof(immoco_lines);
   out[2] = (int32_t)sizeof(immoco_fit);
+  out[3] = (int32_t)sizeof(immoco_grid_csr);
 }
 
-// hashgrid fwd + mlp fwd (x2), fused rows (static + motion groups), colpass, GE, fused adjoint rows,
-// mlp bwd + hashgrid bwd (dense levels + hashed levels: 2 launches) (x2), adam (x2: motion, image)
+// launches per iteration.  Float-atomic path: hashgrid fwd + mlp fwd (x2), gradient entropy, fused rows
+// (static + motion groups), colpass, fused adjoint rows, mlp bwd + hashgrid bwd (dense levels + hashed levels:
+// 2 launches) (x2), adam (x2) = 16.  Deterministic path: the hash-grid backward is ONE gather launch per INR,
+// plus the fixed-point finalize and one partial-sum Adam per INR = 17; with the table update fused into the
+// gather the two table-Adam launches go: 15.
 static int g_fuse_rows = 1;
 extern "C" int immoco_launches_per_iteration(int32_t m) { return m > 0 ? (g_fuse_rows ? 16 : 18) : 10; }
+extern "C" int immoco_launches_per_iteration_mode(int32_t m, int32_t deterministic, int32_t fuse_adam) {
+  if (!deterministic) return immoco_launches_per_iteration(m);
+  const int per_inr = fuse_adam ? 5 : 6;     // hashgrid fwd, mlp fwd, mlp bwd, gather(+adam), adam partials(, adam table)
+  return (m > 0 ? 2 : 1) * per_inr + 1 /*GE*/ + 3 /*rows fwd, colpass, rows bwd*/ + 1 /*finalize*/;
+}
 
 // 1 (default): the static row pass and the pruned motion rows of an iteration are ONE launch (forward) and
 // ONE launch (adjoint); 0: the four separate launches (A/B check)
@@ -258,12 +352,43 @@ struct AuxStream {
   // deferred gradient zeroing (see immoco_fit_run): a third stream and its events
   cudaStream_t zero_stream = nullptr;
   cudaEvent_t adam_i_done = nullptr, zero_start = nullptr, zero_done = nullptr;
+  // deterministic mode: the adjoint row launch finished (the image branch converts the fixed-point plane)
+  cudaEvent_t rows_done = nullptr;
 };
 static std::mutex g_aux_mutex;
 static int g_aux_high_priority = 1;
+static AuxStream g_aux_table[256];
+static int g_aux_used = 0;
+static void aux_destroy(AuxStream& a) {
+  cudaEvent_t ev[8] = {a.fork, a.join_fwd, a.mlp_done, a.join_end, a.adam_i_done, a.zero_start, a.zero_done, a.rows_done};
+  for (auto e : ev)
+    if (e) cudaEventDestroy(e);
+  if (a.stream) cudaStreamDestroy(a.stream);
+  if (a.zero_stream) cudaStreamDestroy(a.zero_stream);
+  a = AuxStream();
+}
+// frees the auxiliary stream sets of the CURRENT device (the caller guarantees no fit is in flight on them)
+extern "C" int immoco_release_streams(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(g_aux_mutex);
+  int freed = 0, kept = 0;
+  for (int i = 0; i < g_aux_used; ++i) {
+    if (g_aux_table[i].dev == dev) {
+      aux_destroy(g_aux_table[i]);
+      ++freed;
+    } else {
+      if (kept != i) g_aux_table[kept] = g_aux_table[i];
+      ++kept;
+    }
+  }
+  for (int i = kept; i < g_aux_used; ++i) g_aux_table[i] = AuxStream();
+  g_aux_used = kept;
+  return freed;
+}
 static AuxStream* aux_for(cudaStream_t owner) {
-  static AuxStream table[256];
-  static int used = 0;
+  AuxStream* table = g_aux_table;
+  int& used = g_aux_used;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(g_aux_mutex);
@@ -281,7 +406,8 @@ static AuxStream* aux_for(cudaStream_t owner) {
       cudaSuccess)
     return nullptr;
   if (cudaStreamCreateWithPriority(&a.zero_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
-  cudaEvent_t* ev[7] = {&a.fork, &a.join_fwd, &a.mlp_done, &a.join_end, &a.adam_i_done, &a.zero_start, &a.zero_done};
+  cudaEvent_t* ev[8] = {&a.fork, &a.join_fwd, &a.mlp_done, &a.join_end, &a.adam_i_done, &a.zero_start, &a.zero_done,
+                        &a.rows_done};
   for (auto e : ev)
     if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   table[used] = a;
@@ -325,17 +451,43 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
   const int64_t mlp_i = (int64_t)wi * 32 + 16 * (int64_t)wi;
   if ((f->n_motion & 3) != 0) return IMMOCO_ERR_BAD_ARG;   // keeps the image half 16-byte aligned
 
+  // ---- reproducible accumulation ---------------------------------------------------------------------
+  const bool det = f->deterministic != 0;
+  const bool fuse_adam = det && f->fuse_adam != 0;
+  if (det) {
+    if (!f->loss_slots || !f->d_image_fx || !f->dc_max_bits || !f->mlp_part_image || !f->csr_image.row_ptr ||
+        !f->csr_image.taps)
+      return IMMOCO_ERR_BAD_ARG;
+    if (M > 0 && (!f->mlp_part_motion || !f->csr_motion.row_ptr || !f->csr_motion.taps)) return IMMOCO_ERR_BAD_ARG;
+    if (f->csr_image.n_points != P || (M > 0 && f->csr_motion.n_points != MP)) return IMMOCO_ERR_BAD_ARG;
+  }
+  int slots[2] = {0, 0};
+  if (f->loss_slots) IMMOCO_TRY(immoco_fit_loss_slots(H, W, slots));
+  const int per_iter = slots[0] + slots[1];
+  const int n_part_i = det ? immoco_mlp_bwd_tc_grid(P) : 0;
+  const int n_part_m = (det && M > 0) ? immoco_mlp_bwd_tc_grid(MP) : 0;
+  float* mom1_m = f->exp_avg;
+  float* mom2_m = f->exp_avg_sq;
+  float* mom1_i = f->exp_avg + f->n_motion;
+  float* mom2_i = f->exp_avg_sq + f->n_motion;
+
   cudaStream_t ms = (cudaStream_t)stream;
   AuxStream* aux = (g_overlap && M > 0) ? aux_for(ms) : nullptr;
   bool forked = false;          // aux currently carries work that `ms` has not joined
   bool zero_pending = false;    // the previous iteration left its gradients for the deferred memset
 
-  const bool fuse_rows = g_fuse_rows != 0;
+  const bool fuse_rows = g_fuse_rows != 0 || det;
   // the fused row launch ADDS into c_tmp; the column pass re-zeroes it for the next iteration
   if (fuse_rows && cudaMemsetAsync(f->c_tmp, 0, (size_t)P * 2 * sizeof(float), ms) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+  // the per-iteration maxima are integer atomicMax targets: clear the ones this call owns
+  if (det && cudaMemsetAsync(f->dc_max_bits + it_begin, 0, (size_t)(it_end - it_begin) * sizeof(uint32_t), ms) != cudaSuccess)
+    return IMMOCO_ERR_BAD_ARG;
 
   for (int it = it_begin; it < it_end; ++it) {
     double* loss = f->loss + 2 * (int64_t)it;
+    double* slots_dc = f->loss_slots ? f->loss_slots + (size_t)it * per_iter : nullptr;
+    double* slots_ge = slots_dc ? slots_dc + slots[0] : nullptr;
+    uint32_t* dmax = det ? f->dc_max_bits + it : nullptr;
     cudaEvent_t* ev = nullptr;
     if (prof && profile_every > 0 && (it % profile_every) == profile_every - 1 && prof->used < prof->capacity)
       ev = prof->ev + (size_t)(prof->used++) * prof_stride(prof);
@@ -353,8 +505,9 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
       forked = true;
     }
     void* is = two ? (void*)aux->stream : stream;       // stream of the image-INR branch
-    // deferred zeroing needs the auxiliary streams; serial (instrumented) iterations zero inside Adam
-    const bool defer_zero = two && g_deferred_zero != 0;
+    // deferred zeroing needs the auxiliary streams; serial (instrumented) iterations zero inside Adam.  The
+    // deterministic path never zeroes: every gradient it consumes is WRITTEN in the same iteration.
+    const bool defer_zero = two && g_deferred_zero != 0 && !det;
     if (zero_pending && !defer_zero) {      // the previous iteration deferred its zeroing, this one cannot
       if (aux) cudaStreamWaitEvent(ms, aux->adam_i_done, 0);
       cudaMemsetAsync(f->grads, 0, (size_t)(f->n_motion + f->n_image) * sizeof(float), ms);
@@ -365,7 +518,7 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     K(0, is, immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is));
     K(1, is, immoco_mlp_fwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->image, P, wi, f->act_image, 0, is));
     // gradient entropy needs the image only; it initialises d_image (lambda folded in)
-    K(7, is, immoco_grad_entropy(f->image, lambdas_host[it], loss + 1, f->d_image, 0, H, W, is));
+    K(7, is, immoco_grad_entropy_slots(f->image, lambdas_host[it], loss + 1, f->d_image, 0, H, W, slots_ge, is));
     if (two) cudaEventRecord(aux->join_fwd, aux->stream);
     K(2, ms, M > 0 ? immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream) : nop());
     if (defer_zero && zero_pending) {
@@ -379,17 +532,23 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     }
     K(3, ms, M > 0 ? immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream) : nop());
     if (two) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
-    if (fuse_rows) {      // slots 4 / 8 (static row passes) are folded into slots 5 / 9
+    if (fuse_rows) {      // slot 4 (static row pass) is folded into slot 5, slot 8 into slot 9
       K(4, ms, nop());
       K(5, ms, immoco_rows_fwd_fused(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
-      K(6, ms, immoco_colpass_loss_zero(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
-      K(8, ms, nop());
+      K(6, ms, immoco_colpass_loss_zero(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, slots_dc, dmax, stream));
       K(9, ms, immoco_rows_bwd_fused(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->d_image,
-                                     f->d_disp, H, W, stream));
+                                     f->d_disp, H, W, det ? f->d_image_fx : nullptr, dmax, stream));
+      if (det) {
+        // d_image += the fixed-point plane; on the image branch (it is the only consumer), beside MLPm_b
+        if (two) { cudaEventRecord(aux->rows_done, ms); cudaStreamWaitEvent(aux->stream, aux->rows_done, 0); }
+        K(8, is, immoco_d_image_finalize(f->d_image, f->d_image_fx, dmax, H, W, is));
+      } else {
+        K(8, ms, nop());
+      }
     } else {
       K(4, ms, immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
       K(5, ms, immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
-      K(6, ms, immoco_colpass_loss(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, stream));
+      K(6, ms, immoco_colpass_loss_slots(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, slots_dc, nullptr, stream));
       // ---- backward ----------------------------------------------------------------------------
       K(8, ms, immoco_rows_static(f->d_c, f->d_image, H, W, f->tw_w, f->lines.static_w, nullptr, 1, true, stream));
       K(9, ms, M > 0 ? immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
@@ -398,6 +557,43 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     if (defer_zero && zero_pending) {      // first accumulation into the gradients of this iteration
       cudaStreamWaitEvent(ms, aux->zero_done, 0);
       zero_pending = false;
+    }
+    if (det) {
+      // ---- backward + update, reproducible: per-CTA weight-gradient blocks, row-sorted gathers -----------
+      K(10, ms, M > 0 ? immoco_mlp_bwd_partials(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion,
+                                                f->mlp_part_motion, MP, wm, f->act_motion, stream) : nop());
+      if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
+      if (fuse_adam) {
+        K(11, ms, M > 0 ? immoco_hashgrid_bwd_csr_adam(&f->grid_motion, &f->csr_motion, f->d_enc_motion, pm + mlp_m,
+                                                       mom1_m + mlp_m, mom2_m + mlp_m, nullptr, f->lr, f->beta1,
+                                                       f->beta2, f->eps, it + 1, stream) : nop());
+      } else {
+        K(11, ms, M > 0 ? immoco_hashgrid_bwd_csr(&f->grid_motion, &f->csr_motion, f->d_enc_motion, gm + mlp_m, stream) : nop());
+      }
+      K(12, is, immoco_mlp_bwd_partials(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image,
+                                        f->mlp_part_image, P, wi, f->act_image, is));
+      if (fuse_adam) {
+        K(13, is, immoco_hashgrid_bwd_csr_adam(&f->grid_image, &f->csr_image, f->d_enc_image, pi + mlp_i, mom1_i + mlp_i,
+                                               mom2_i + mlp_i, nullptr, f->lr, f->beta1, f->beta2, f->eps, it + 1, is));
+      } else {
+        K(13, is, immoco_hashgrid_bwd_csr(&f->grid_image, &f->csr_image, f->d_enc_image, gi + mlp_i, is));
+      }
+      if (ev) cudaEventRecord(ev[1 + 2 * 14], ms);
+      if (M > 0) {
+        IMMOCO_TRY(immoco_adam_step_partials(pm, f->mlp_part_motion, n_part_m, mom1_m, mom2_m, mlp_m, f->lr, f->beta1,
+                                             f->beta2, f->eps, it + 1, stream));
+        if (!fuse_adam)
+          IMMOCO_TRY(immoco_adam_step(pm + mlp_m, gm + mlp_m, mom1_m + mlp_m, mom2_m + mlp_m, f->n_motion - mlp_m, f->lr,
+                                      f->beta1, f->beta2, f->eps, it + 1, 0, stream));
+      }
+      if (ev) { cudaEventRecord(ev[2 + 2 * 14], ms); cudaEventRecord(ev[1 + 2 * 15], (cudaStream_t)is); }
+      IMMOCO_TRY(immoco_adam_step_partials(pi, f->mlp_part_image, n_part_i, mom1_i, mom2_i, mlp_i, f->lr, f->beta1,
+                                           f->beta2, f->eps, it + 1, is));
+      if (!fuse_adam)
+        IMMOCO_TRY(immoco_adam_step(pi + mlp_i, gi + mlp_i, mom1_i + mlp_i, mom2_i + mlp_i, f->n_image - mlp_i, f->lr,
+                                    f->beta1, f->beta2, f->eps, it + 1, 0, is));
+      if (ev) cudaEventRecord(ev[2 + 2 * 15], (cudaStream_t)is);
+      continue;
     }
     K(10, ms, M > 0 ? immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
                                      gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream) : nop());
@@ -421,6 +617,11 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
   if (forked) {
     cudaEventRecord(aux->join_end, aux->stream);
     cudaStreamWaitEvent(ms, aux->join_end, 0);
+  }
+  if (f->loss_slots) {      // per-CTA loss slots of this call's iterations -> f->loss, added in slot order
+    const int n = 2 * (it_end - it_begin);
+    loss_reduce_kernel<<<(n + 127) / 128, 128, 0, ms>>>(f->loss_slots, per_iter, slots[0], f->loss, it_begin, it_end);
+    IMMOCO_LAUNCH_CHECK();
   }
   return 0;
 }

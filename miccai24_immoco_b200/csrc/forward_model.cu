@@ -28,16 +28,44 @@ __device__ __forceinline__ int wrap_mod_fast(int a, int n, float inv_n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Reproducible accumulation of the image cotangent (deterministic mode).  The adjoint row passes scatter
+// into d_image from many CTAs; float atomics make the sum depend on arrival order.  Instead every
+// contribution is converted to 64-bit fixed point and added with integer atomics (associative ->
+// order-free), then converted back once (d_image_finalize_kernel).  The scale is a power of two chosen per
+// iteration from mx = max |component of d_c| (column pass, integer atomicMax): a contribution is a (pruned)
+// row DFT of at most W weighted entries, |c| <= 4 * W2 * mx with W2 = W rounded up to a power of two and 4 =
+// slack for mask weights; 2^20 contributions may pile up on one pixel: scale = 2^(62 - 20 - 2 - log2 W2 - e)
+// with mx < 2^e.  A typical contribution (~ sqrt(W) * mx) keeps ~2^-35 relative resolution, far below fp32.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fx_exponent(uint32_t dmax_bits, int W) {
+  const float mx = __uint_as_float(dmax_bits);
+  int e = 0;
+  if (mx > 0.0f && mx <= 3.0e38f) e = ilogbf(mx) + 1;
+  const int lw = 32 - __clz(W - 1);
+  return 40 - lw - e;
+}
+__device__ __forceinline__ double pow2_double(int p) {
+  return __longlong_as_double((long long)(1023 + p) << 52);
+}
+__device__ __forceinline__ void fx_add(long long* __restrict__ fx, size_t idx, float c, double sc) {
+  const long long q = __double2ll_rn((double)c * sc);
+  if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(fx) + idx, (unsigned long long)q);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row pass: centred 1-D FFT along W of `rows` rows.
 //   out[r][l] (+)= scale * out_w[l] * sum_j in_w[j] * in[r][j] * exp(-/+ 2 pi i (l-W/2)(j-W/2)/W)
 // ------------------------------------------------------------------------------------------------
 // ATOMIC: the result is ADDED with float atomics (entries whose output weight is zero are skipped) -- used
 // by the fused launches below, where CTAs of the pruned motion rows add into the same buffer concurrently.
-template <bool INV, bool ATOMIC>
+// MODE 0: plain store (optionally read-modify-write), 1: float atomics, 2: 64-bit fixed-point atomics into `fx`
+template <bool INV, int MODE>
 __device__ __forceinline__ void rows_body(const float2* __restrict__ in, float2* __restrict__ out, int rows, int W,
                                           const FftPlan& plan, const float2* __restrict__ tw_g,
                                           const float* __restrict__ in_w, const float* __restrict__ out_w,
-                                          float scale, int accumulate, int cta) {
+                                          float scale, int accumulate, int cta, long long* __restrict__ fx = nullptr,
+                                          double fx_sc = 0.0) {
+  constexpr bool ATOMIC = MODE == 1;
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* a = tw + W;
@@ -63,7 +91,11 @@ __device__ __forceinline__ void rows_body(const float2* __restrict__ in, float2*
     if (out_w) s *= __ldg(out_w + l);
     v.x *= s; v.y *= s;
     float2* o = out + (size_t)(r0 + r) * W + l;
-    if (ATOMIC) {
+    if (MODE == 2) {
+      const size_t gi = 2 * ((size_t)(r0 + r) * W + l);
+      fx_add(fx, gi, v.x, fx_sc);
+      fx_add(fx, gi + 1, v.y, fx_sc);
+    } else if (ATOMIC) {
       if (s != 0.0f) atomicAdd(o, v);
     } else {
       if (accumulate) { const float2 p = *o; v.x += p.x; v.y += p.y; }
@@ -79,7 +111,7 @@ fft_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int row
                 const float* __restrict__ in_w, const float* __restrict__ out_w, float scale,
                 int accumulate) {
   pdl_wait();
-  rows_body<INV, false>(in, out, rows, W, plan, tw_g, in_w, out_w, scale, accumulate, blockIdx.x);
+  rows_body<INV, 0>(in, out, rows, W, plan, tw_g, in_w, out_w, scale, accumulate, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -138,10 +170,12 @@ __global__ void __launch_bounds__(kThreads)
 colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ k_in,
                     float2* __restrict__ k_out, float2* __restrict__ d_c, double* __restrict__ loss_acc,
                     int H, int W, const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
-                    float2* __restrict__ zero_after_load) {
+                    float2* __restrict__ zero_after_load, double* __restrict__ loss_slots,
+                    uint32_t* __restrict__ dmax_bits) {
   pdl_wait();
   extern __shared__ __align__(16) float2 sm2[];
   __shared__ float red[kThreads / 32];
+  __shared__ float redmax[kThreads / 32];
   const int HP = H + 1;
   float2* tw = sm2;
   float2* a = tw + H;
@@ -200,14 +234,31 @@ colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ 
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int wv = 0; wv < kThreads / 32; ++wv) s += (double)red[wv];
-    atomicAdd(loss_acc, s);
+    // fit loop: this CTA's slot, added in slot order at the end of the call (reproducible); else one atomic
+    if (loss_slots) loss_slots[blockIdx.x] = s;
+    else atomicAdd(loss_acc, s);
   }
   const float2* adj = fft_smem<true>(res, other, nc, HP, plan, tw);
+  float mx = 0.0f;
   for (int idx = threadIdx.x; idx < H * CPC; idx += kThreads) {
     const int i = idx / CPC, c = idx - i * CPC;
     if (c < nc) {
       int ii = i + half; if (ii >= H) ii -= H;
-      d_c[(size_t)i * W + l0 + c] = adj[c * HP + ii];
+      const float2 v = adj[c * HP + ii];
+      d_c[(size_t)i * W + l0 + c] = v;
+      mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+    }
+  }
+  if (dmax_bits) {      // largest cotangent component: scale of the fixed-point image-cotangent accumulation
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) redmax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.0f;
+      for (int wv = 0; wv < kThreads / 32; ++wv) m = fmaxf(m, redmax[wv]);
+      if (!(m <= 3.0e38f)) m = 3.0e38f;                 // NaN / inf (diverged fit): saturate
+      atomicMax(dmax_bits, __float_as_uint(m));         // non-negative floats order like their bit patterns
     }
   }
 }
@@ -305,7 +356,7 @@ rows_fwd_fused_kernel(const float2* __restrict__ image, const float2* __restrict
   pdl_wait();
   if (blockIdx.y == 0) {
     if ((int)blockIdx.x * kRowsPerCta >= H) return;
-    rows_body<false, true>(image, c_out, H, W, plan, tw_g, nullptr, lines.static_w, 1.0f, 0, blockIdx.x);
+    rows_body<false, 1>(image, c_out, H, W, plan, tw_g, nullptr, lines.static_w, 1.0f, 0, blockIdx.x);
   } else {
     motion_rows_fwd_body(image, disp, ident, lines, tw_g, c_out, H, W, blockIdx.x, (int)blockIdx.y - 1);
   }
@@ -313,11 +364,23 @@ rows_fwd_fused_kernel(const float2* __restrict__ image, const float2* __restrict
 
 // Adjoint of the kernel above: pruned inverse row DFT -> d(moved row) -> scatter into d_image
 // (grid_sampler_2d_backward) and the cotangent of the PRE-tanh displacement.
+template <bool DET>
 __device__ __forceinline__ void motion_rows_bwd_body(const float2* __restrict__ d_c, const float2* __restrict__ image,
                                                      const float2* __restrict__ disp, const float2* __restrict__ ident,
                                                      const immoco_lines& lines, const float2* __restrict__ tw_g,
                                                      float2* __restrict__ d_image, float2* __restrict__ d_disp,
-                                                     int pre_tanh, int H, int W, int i, int m) {
+                                                     int pre_tanh, int H, int W, int i, int m,
+                                                     long long* __restrict__ fx = nullptr, double fx_sc = 0.0) {
+  // scatter of one tap's contribution: float2 atomic, or two fixed-point atomics (deterministic mode)
+  auto scatter = [&](int y, int x, float w, float gr, float gi) {
+    const size_t idx = (size_t)y * W + x;
+    if (DET) {
+      fx_add(fx, 2 * idx, w * gr, fx_sc);
+      fx_add(fx, 2 * idx + 1, w * gi, fx_sc);
+    } else {
+      atomicAdd(d_image + idx, make_float2(w * gr, w * gi));
+    }
+  };
   extern __shared__ __align__(16) float2 sm2[];
   float2* tw = sm2;
   float2* gl = tw + W;
@@ -355,33 +418,25 @@ __device__ __forceinline__ void motion_rows_bwd_body(const float2* __restrict__ 
     const bool iny0 = (unsigned)y0 < (unsigned)H, iny1 = (unsigned)y1 < (unsigned)H;
     float gix = 0.f, giy = 0.f;
     if (iny0 && inx0) {
-      float2* p = d_image + (size_t)y0 * W + x0;
-      const float w = t.wx0 * t.wy0;
-      atomicAdd(p, make_float2(w * gr, w * gi));
+      scatter(y0, x0, t.wx0 * t.wy0, gr, gi);
       const float2 v = __ldg(image + (size_t)y0 * W + x0);
       const float dot = v.x * gr + v.y * gi;
       gix -= dot * t.wy0; giy -= dot * t.wx0;
     }
     if (iny0 && inx1) {
-      float2* p = d_image + (size_t)y0 * W + x1;
-      const float w = t.wx1 * t.wy0;
-      atomicAdd(p, make_float2(w * gr, w * gi));
+      scatter(y0, x1, t.wx1 * t.wy0, gr, gi);
       const float2 v = __ldg(image + (size_t)y0 * W + x1);
       const float dot = v.x * gr + v.y * gi;
       gix += dot * t.wy0; giy -= dot * t.wx1;
     }
     if (iny1 && inx0) {
-      float2* p = d_image + (size_t)y1 * W + x0;
-      const float w = t.wx0 * t.wy1;
-      atomicAdd(p, make_float2(w * gr, w * gi));
+      scatter(y1, x0, t.wx0 * t.wy1, gr, gi);
       const float2 v = __ldg(image + (size_t)y1 * W + x0);
       const float dot = v.x * gr + v.y * gi;
       gix -= dot * t.wy1; giy += dot * t.wx0;
     }
     if (iny1 && inx1) {
-      float2* p = d_image + (size_t)y1 * W + x1;
-      const float w = t.wx1 * t.wy1;
-      atomicAdd(p, make_float2(w * gr, w * gi));
+      scatter(y1, x1, t.wx1 * t.wy1, gr, gi);
       const float2 v = __ldg(image + (size_t)y1 * W + x1);
       const float dot = v.x * gr + v.y * gi;
       gix += dot * t.wy1; giy += dot * t.wx1;
@@ -399,24 +454,45 @@ motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict_
                        float2* __restrict__ d_image, float2* __restrict__ d_disp, int pre_tanh, int H,
                        int W) {
   pdl_wait();
-  motion_rows_bwd_body(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, pre_tanh, H, W, blockIdx.x, blockIdx.y);
+  motion_rows_bwd_body<false>(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, pre_tanh, H, W, blockIdx.x, blockIdx.y);
 }
 
 // Fused adjoint row launch of the fit loop: blockIdx.y == 0 -> adjoint static row pass, ADDED into d_image
 // with float atomics; blockIdx.y == 1 + m -> adjoint of movement group m (scatter into d_image, d_disp).
+// DET: every contribution goes to the 64-bit fixed-point plane `fx` (scale from dmax_bits, see fx_exponent);
+// d_image itself (it holds the gradient-entropy term) is only touched by d_image_finalize_kernel afterwards.
+template <bool DET>
 __global__ void __launch_bounds__(kThreads)
 rows_bwd_fused_kernel(const float2* __restrict__ d_c, const float2* __restrict__ image,
                       const float2* __restrict__ disp, const float2* __restrict__ ident,
                       const __grid_constant__ immoco_lines lines, const __grid_constant__ FftPlan plan,
                       const float2* __restrict__ tw_g, float2* __restrict__ d_image,
-                      float2* __restrict__ d_disp, int H, int W) {
+                      float2* __restrict__ d_disp, int H, int W, long long* __restrict__ fx,
+                      const uint32_t* __restrict__ dmax_bits) {
   pdl_wait();
+  const double sc = DET ? pow2_double(fx_exponent(*dmax_bits, W)) : 0.0;
   if (blockIdx.y == 0) {
     if ((int)blockIdx.x * kRowsPerCta >= H) return;
-    rows_body<true, true>(d_c, d_image, H, W, plan, tw_g, lines.static_w, nullptr, 1.0f, 1, blockIdx.x);
+    rows_body<true, DET ? 2 : 1>(d_c, d_image, H, W, plan, tw_g, lines.static_w, nullptr, 1.0f, 1, blockIdx.x, fx, sc);
   } else {
-    motion_rows_bwd_body(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, 1, H, W, blockIdx.x,
-                         (int)blockIdx.y - 1);
+    motion_rows_bwd_body<DET>(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, 1, H, W, blockIdx.x,
+                              (int)blockIdx.y - 1, fx, sc);
+  }
+}
+
+// d_image += fixed-point plane (converted back with the iteration's scale); the plane is re-zeroed for the
+// next iteration.  One rounding per element whatever order the contributions arrived in.
+__global__ void __launch_bounds__(kThreads)
+d_image_finalize_kernel(float* __restrict__ d_image, long long* __restrict__ fx, const uint32_t* __restrict__ dmax_bits,
+                        int n, int W) {
+  pdl_wait();
+  const double inv = pow2_double(-fx_exponent(*dmax_bits, W));
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const long long q = fx[i];
+    if (q != 0) {
+      d_image[i] += (float)((double)q * inv);
+      fx[i] = 0;
+    }
   }
 }
 
@@ -433,7 +509,7 @@ __device__ __forceinline__ float ge_dloss_dg(float g) {
 
 __global__ void __launch_bounds__(kThreads)
 grad_entropy_kernel(const float2* __restrict__ img, float grad_scale, double* __restrict__ loss_acc,
-                    float2* __restrict__ d_img, int accumulate, int H, int W) {
+                    float2* __restrict__ d_img, int accumulate, int H, int W, double* __restrict__ loss_slots) {
   pdl_wait();
   __shared__ float red[kThreads / 32];
   const int P = H * W;
@@ -483,7 +559,8 @@ grad_entropy_kernel(const float2* __restrict__ img, float grad_scale, double* __
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int wv = 0; wv < kThreads / 32; ++wv) s += (double)red[wv];
-    atomicAdd(loss_acc, s);
+    if (loss_slots) loss_slots[blockIdx.x] = s;
+    else atomicAdd(loss_acc, s);
   }
 }
 
@@ -615,24 +692,30 @@ extern "C" int immoco_forward_model_bwd(const float* d_k, const float* image, co
   return launch_motion_bwd(c_tmp, image, disp, ident, lines, tw_w, d_image, d_disp, pre_tanh, h, w, s);
 }
 
+// columns per CTA of the fused column pass: 4 (64-byte segments) when that still gives every SM a CTA, else 2
+// (narrow images: 320 columns -> 80 CTAs of 4)
+static int colpass_cpc(int w) { return ((w + kColsPerCta - 1) / kColsPerCta >= IMMOCO_NUM_SMS) ? kColsPerCta : 2; }
+static int colpass_grid(int w) { const int cpc = colpass_cpc(w); return (w + cpc - 1) / cpc; }
+static int grad_entropy_grid(int h, int w) { return (h * w + kThreads - 1) / kThreads; }
+
 static int colpass_launch(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
-                          const float* tw_h, int32_t h, int32_t w, float* zero_after_load, void* stream) {
+                          const float* tw_h, int32_t h, int32_t w, float* zero_after_load, double* loss_slots,
+                          uint32_t* dmax_bits, void* stream) {
   const Plans p = make_plans(h, w);
   if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
   const size_t smem = cols_smem(h);
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
-  if ((w + kColsPerCta - 1) / kColsPerCta >= IMMOCO_NUM_SMS) {
+  const int grid = colpass_grid(w);
+  if (colpass_cpc(w) == kColsPerCta) {
     allow_smem(colpass_loss_kernel<kColsPerCta>, smem);
-    const int grid = (w + kColsPerCta - 1) / kColsPerCta;
     immoco_launch(colpass_loss_kernel<kColsPerCta>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream,
         (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
-        (const float2*)tw_h, (float2*)zero_after_load);
-  } else {       // narrow images (320 columns -> 80 CTAs of 4): 2 columns per CTA so every SM has work
+        (const float2*)tw_h, (float2*)zero_after_load, loss_slots, dmax_bits);
+  } else {
     allow_smem(colpass_loss_kernel<2>, smem);
-    const int grid = (w + 1) / 2;
     immoco_launch(colpass_loss_kernel<2>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream,
         (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
-        (const float2*)tw_h, (float2*)zero_after_load);
+        (const float2*)tw_h, (float2*)zero_after_load, loss_slots, dmax_bits);
   }
   IMMOCO_LAUNCH_CHECK();
   return 0;
@@ -641,23 +724,47 @@ static int colpass_launch(const float* c, const float* k_in, float* k_out, float
 extern "C" int immoco_colpass_loss(const float* c, const float* k_in, float* k_out, float* d_c,
                                    double* loss_acc, const float* tw_h, int32_t h, int32_t w,
                                    void* stream) {
-  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, nullptr, stream);
+  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, nullptr, nullptr, nullptr, stream);
 }
-// fit.cu: column pass that leaves its input buffer zeroed for the next iteration's fused row launch
+// fit.cu: column pass that leaves its input buffer zeroed for the next iteration's fused row launch; the loss
+// goes to per-CTA slots when `loss_slots` is given, the largest cotangent component to *dmax_bits when given
 int immoco_colpass_loss_zero(float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
-                             const float* tw_h, int h, int w, void* stream) {
-  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, c, stream);
+                             const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream) {
+  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, c, loss_slots, dmax_bits, stream);
+}
+int immoco_colpass_loss_slots(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
+                              const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream) {
+  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, nullptr, loss_slots, dmax_bits, stream);
 }
 
+int immoco_grad_entropy_slots(const float* image, float grad_scale, double* loss_acc, float* d_image,
+                              int accumulate, int h, int w, double* loss_slots, void* stream) {
+  if (h < 1 || w < 1) return IMMOCO_ERR_BAD_ARG;
+  immoco_launch(grad_entropy_kernel, dim3(grad_entropy_grid(h, w)), dim3(kThreads), 0, (cudaStream_t)stream,
+                (const float2*)image, grad_scale, loss_acc, (float2*)d_image, accumulate, h, w, loss_slots);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
 extern "C" int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc,
                                    float* d_image, int32_t accumulate, int32_t h, int32_t w,
                                    void* stream) {
-  if (h < 1 || w < 1) return IMMOCO_ERR_BAD_ARG;
-  const int P = h * w;
-  int grid = (P + kThreads - 1) / kThreads;
-  immoco_launch(grad_entropy_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const float2*)image, grad_scale,
-                                                                  loss_acc, (float2*)d_image,
-                                                                  accumulate, h, w);
+  return immoco_grad_entropy_slots(image, grad_scale, loss_acc, d_image, accumulate, h, w, nullptr, stream);
+}
+
+extern "C" int immoco_fit_loss_slots(int32_t h, int32_t w, int32_t out[2]) {
+  if (h < 2 || w < 2 || !out) return IMMOCO_ERR_BAD_ARG;
+  out[0] = colpass_grid(w);
+  out[1] = grad_entropy_grid(h, w);
+  return 0;
+}
+
+// d_image += the fixed-point cotangent plane of this iteration (deterministic mode), plane re-zeroed
+int immoco_d_image_finalize(float* d_image, int64_t* fx, const uint32_t* dmax_bits, int h, int w, void* stream) {
+  const int n = 2 * h * w;
+  int grid = (n + kThreads - 1) / kThreads;
+  if (grid > IMMOCO_NUM_SMS * 8) grid = IMMOCO_NUM_SMS * 8;
+  immoco_launch(d_image_finalize_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, d_image, (long long*)fx,
+                dmax_bits, n, w);
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
@@ -694,20 +801,29 @@ int immoco_rows_fwd_fused(const float* image, const float* disp, const float* id
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
+// fx != nullptr: deterministic mode (fixed-point accumulation, d_image itself untouched until the finalize)
 int immoco_rows_bwd_fused(const float* d_c, const float* image, const float* disp, const float* ident,
                           const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp, int h, int w,
-                          void* stream) {
+                          int64_t* fx, const uint32_t* dmax_bits, void* stream) {
   const Plans p = make_plans(h, w);
   if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  if (fx && !dmax_bits) return IMMOCO_ERR_BAD_ARG;
   size_t smem = (size_t)(w + 2 * kRowsPerCta * w) * sizeof(float2);
   const size_t smem_m = (size_t)w * sizeof(float2) + (size_t)lines->max_lines * (sizeof(float2) + sizeof(int));
   if (smem_m > smem) smem = smem_m;
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
-  allow_smem(rows_bwd_fused_kernel, smem);
   dim3 grid(h, 1 + lines->n_groups);
-  immoco_launch(rows_bwd_fused_kernel, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)d_c,
-                (const float2*)image, (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w,
-                (float2*)d_image, (float2*)d_disp, h, w);
+  if (fx) {
+    allow_smem(rows_bwd_fused_kernel<true>, smem);
+    immoco_launch(rows_bwd_fused_kernel<true>, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)d_c,
+                  (const float2*)image, (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w,
+                  (float2*)d_image, (float2*)d_disp, h, w, (long long*)fx, dmax_bits);
+  } else {
+    allow_smem(rows_bwd_fused_kernel<false>, smem);
+    immoco_launch(rows_bwd_fused_kernel<false>, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)d_c,
+                  (const float2*)image, (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w,
+                  (float2*)d_image, (float2*)d_disp, h, w, (long long*)nullptr, (const uint32_t*)nullptr);
+  }
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }

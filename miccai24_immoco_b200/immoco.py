@@ -247,6 +247,61 @@ def _row_permutation(grid, swizzle, dev) -> torch.Tensor:
     return _ROW_PERM_CACHE[key]
 
 
+_CSR_CACHE: dict = {}
+
+
+class GridCsr:
+    """Row-sorted tap list of one hash grid over one constant coordinate set (include/immoco_b200.h, section
+    1b): built once by ``immoco_hashgrid_csr_build`` and shared by every fit of the same shape -- the gather
+    form of the hash-grid backward pass that makes a fit bit-reproducible."""
+
+    def __init__(self, grid, desc, coords: torch.Tensor):
+        lib = nat.lib()
+        dev = coords.device
+        n = int(coords.shape[0])
+        self.n_points = n
+        self.n_taps = n * (1 << grid.n_dims) * grid.n_levels
+        self.row_ptr = torch.empty(grid.n_rows + 1, dtype=torch.int32, device=dev)
+        self.taps = torch.empty((max(self.n_taps, 1), 2), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            need = int(lib.immoco_hashgrid_csr_workspace_bytes(C.byref(desc), n))
+            if need < 0:
+                raise nat.NativeError("hashgrid_csr_workspace_bytes: rejected arguments")
+            work = torch.empty(need, dtype=torch.uint8, device=dev)
+            nat.check(lib.immoco_hashgrid_csr_build(C.byref(desc), coords.data_ptr(), n, self.row_ptr.data_ptr(),
+                                                    self.taps.data_ptr(), work.data_ptr(), need,
+                                                    torch.cuda.current_stream(dev).cuda_stream), "hashgrid_csr_build")
+            work.record_stream(torch.cuda.current_stream(dev))
+            # engines on other streams (reconstruct_batch slots) wait for the build before their first gather
+            self.ready = torch.cuda.Event()
+            self.ready.record(torch.cuda.current_stream(dev))
+
+    def struct(self) -> nat.GridCsr:
+        c = nat.GridCsr()
+        c.row_ptr = self.row_ptr.data_ptr()
+        c.taps = self.taps.data_ptr()
+        c.n_taps = self.n_taps
+        c.n_points = self.n_points
+        return c
+
+
+def _cached_csr(kind: str, shape, grid, swizzle, coords: torch.Tensor) -> GridCsr:
+    key = (kind, tuple(int(v) for v in shape), str(coords.device), grid.n_dims, grid.offsets, tuple(swizzle))
+    csr = _CSR_CACHE.get(key)
+    if csr is None:
+        csr = GridCsr(grid, grid.desc(swizzle), coords)
+        _CSR_CACHE[key] = csr
+    torch.cuda.current_stream(coords.device).wait_event(csr.ready)
+    return csr
+
+
+def clear_caches() -> None:
+    """Drops the per-shape device caches (coordinates, row permutations, tap lists)."""
+    _CSR_CACHE.clear()
+    _ROW_PERM_CACHE.clear()
+    _COORD_CACHE.clear()
+
+
 class FitEngine:
     """Device state + native loop for ONE slice: both INRs' parameters, gradients and Adam moments
     live in one flat fp32 vector [motion | image]; every iteration is 16 kernel launches issued by
@@ -257,9 +312,17 @@ class FitEngine:
     Parameters are permuted on the way in (constructor, ``reset``) and back in ``write_back``; everything
     outside the engine sees the reference's layout.  ``row_swizzle=False`` keeps the reference layout."""
 
-    def __init__(self, model: IMMoCo, max_iters: int, row_swizzle: bool = True):
+    def __init__(self, model: IMMoCo, max_iters: int, row_swizzle: bool = True,
+                 deterministic: Optional[bool] = None, fuse_adam: Optional[bool] = None):
+        """``deterministic`` (default: the library-wide ``immoco_get_deterministic()``): bit-reproducible fit --
+        hash-grid backward as a row-sorted gather over a tap list built once per shape, MLP weight gradients
+        as per-CTA blocks added in CTA order, image cotangent in 64-bit fixed point.  ``fuse_adam`` (default:
+        on in deterministic mode): the table rows are updated inside the gather kernel."""
         self.model = model
         dev = model.device
+        lib = nat.lib()
+        self.deterministic = bool(lib.immoco_get_deterministic()) if deterministic is None else bool(deterministic)
+        self.fuse_adam = self.deterministic and (True if fuse_adam is None else bool(fuse_adam))
         h, w, m = model.x, model.num_lines, model.num_movements
         p, mp = h * w, h * w * m
         img, mot = model.image_inr, model.motion_inr
@@ -271,7 +334,7 @@ class FitEngine:
         self._perm: Optional[torch.Tensor] = None
         self._n_mlp_motion = mot.mlp.n_params
         if row_swizzle and m > 0:
-            u = torch.unique(model.input_grid[:, 0]).cpu().numpy()
+            u = torch.linspace(-1, 1, m).numpy()        # dim-0 values of make_grids, known without a device sync
             swz = mot.grid.row_swizzle(u) if u.size <= 64 else ()
             if any(swz):
                 self._swizzle = swz
@@ -319,6 +382,29 @@ class FitEngine:
         f.c_tmp, f.d_c, f.k_out = self.c_tmp.data_ptr(), self.d_c.data_ptr(), self.k_out.data_ptr()
         f.loss = self.loss.data_ptr()
         f.lr, f.beta1, f.beta2, f.eps = 1e-2, 0.9, 0.999, 1e-8
+        # per-CTA loss slots (both modes: no floating-point atomics on the loss trace)
+        slots = (C.c_int32 * 2)()
+        nat.check(lib.immoco_fit_loss_slots(h, w, slots), "fit_loss_slots")
+        self.loss_slots = torch.zeros((max_iters, slots[0] + slots[1]), dtype=torch.float64, device=dev)
+        f.loss_slots = self.loss_slots.data_ptr()
+        f.deterministic, f.fuse_adam = int(self.deterministic), int(self.fuse_adam)
+        if self.deterministic:
+            with torch.cuda.device(dev):
+                self.csr_image = _cached_csr("identity", (h, w), img.grid, (), model._ident)
+                f.csr_image = self.csr_image.struct()
+                n_part_i = lib.immoco_mlp_bwd_partial_count(p)
+                self.mlp_part_image = torch.zeros((n_part_i, img.mlp.n_params), **f32)
+                f.mlp_part_image = self.mlp_part_image.data_ptr()
+                if m > 0:
+                    self.csr_motion = _cached_csr("motion", (m, h, w), mot.grid, self._swizzle, self.coords_motion)
+                    f.csr_motion = self.csr_motion.struct()
+                    n_part_m = lib.immoco_mlp_bwd_partial_count(mp)
+                    self.mlp_part_motion = torch.zeros((n_part_m, mot.mlp.n_params), **f32)
+                    f.mlp_part_motion = self.mlp_part_motion.data_ptr()
+            self.d_image_fx = torch.zeros((h, w, 2), dtype=torch.int64, device=dev)
+            self.dc_max_bits = torch.zeros(max_iters, dtype=torch.int32, device=dev)
+            f.d_image_fx = self.d_image_fx.data_ptr()
+            f.dc_max_bits = self.dc_max_bits.data_ptr()
         self.fit = f
         self.launches = 0
 
@@ -349,6 +435,8 @@ class FitEngine:
         self.params[self.n_motion:].copy_(image_params)
         self.state.zero_()
         self.loss.zero_()
+        if self.deterministic:
+            self.d_image_fx.zero_()
 
     def run(self, lambdas: List[float], learning_rate: float, it_begin: int = 0,
             it_end: Optional[int] = None, profile=None, profile_every: int = 0) -> None:
@@ -357,9 +445,13 @@ class FitEngine:
             raise ValueError("more iterations than the loss buffer holds")
         self.fit.lr = float(learning_rate)
         lam = (C.c_float * len(lambdas))(*[float(v) for v in lambdas])
-        nat.check(nat.lib().immoco_fit_run(C.byref(self.fit), it_begin, it_end, lam, _stream(),
-                                           profile, profile_every), "fit_run")
-        self.launches += (it_end - it_begin) * nat.lib().immoco_launches_per_iteration(self.fit.m)
+        dev = self.model.device
+        with torch.cuda.device(dev):        # the library keys its auxiliary streams on the current device
+            nat.check(nat.lib().immoco_fit_run(C.byref(self.fit), it_begin, it_end, lam,
+                                               torch.cuda.current_stream(dev).cuda_stream, profile, profile_every),
+                      "fit_run")
+        self.launches += (it_end - it_begin) * nat.lib().immoco_launches_per_iteration_mode(
+            self.fit.m, int(self.deterministic), int(self.fuse_adam))
 
     def loss_trace(self, lambdas: List[float]) -> np.ndarray:
         """fp32 loss of every iteration: mse + fp32(lambda) * GE, assembled like the reference
@@ -379,14 +471,16 @@ class FitEngine:
 
 def imcoco_motion_correction(kspace_corr, masks, iters=200, learning_rate=1e-2, lambda_ge=1e-2,
                              debug=False, *, image_params=None, motion_params=None,
-                             kmax: float = 16000.0, variant: str = "main", return_trace: bool = False):
+                             kmax: float = 16000.0, variant: str = "main", return_trace: bool = False,
+                             deterministic: Optional[bool] = None):
     """Fit Image INR + Motion INR to one motion-corrupted k-space (immoco.py:116-206).
 
     Positional signature and defaults are the reference's.  Returns ``(image_prior,
     kspace_foward_model)`` of the LAST iteration's forward pass, i.e. before the last Adam step
     (SURVEY Q4), as detached complex64 CUDA tensors in the 16000-normalised scale (Q5).
     Keyword-only extras: injected initial parameters (tests), ``kmax``/``variant`` for the
-    downstream copy's constants (test_immoco_downstream.py:152,189), ``return_trace``.
+    downstream copy's constants (test_immoco_downstream.py:152,189), ``return_trace``, ``deterministic``
+    (bit-reproducible fit; default = ``immoco_get_deterministic()``, see ``FitEngine``).
     """
     if not torch.cuda.is_available():
         raise RuntimeError("imcoco_motion_correction needs a CUDA device (no CPU fallback)")
@@ -404,7 +498,7 @@ def imcoco_motion_correction(kspace_corr, masks, iters=200, learning_rate=1e-2, 
         print(f"Scale: {scale:.4f}")
         print(f"Kspace input: {kspace_input.abs().min().item():.4f}, {kspace_input.abs().max().item():.4f}")
     lambdas = lambda_schedule(iters, lambda_ge, variant)
-    engine = FitEngine(model, max(iters, 1))
+    engine = FitEngine(model, max(iters, 1), deterministic=deterministic)
     engine.set_kspace(kspace_input)
     engine.run(lambdas, learning_rate)
     image_prior = torch.view_as_complex(engine.image.clone())

@@ -1,7 +1,8 @@
 // INR MLPs: out = W2[:2] . act(W1 . enc), one hidden layer, no biases.
 // Replaces the network half of tcnn.NetworkWithInputEncoding (src/models/immoco.py:11-25,60-65).
 //
-// fp32 SIMT implementation (exact-fp32 parity anchor).  A CTA owns tiles of 128 points; the hidden
+// TEST-SIDE CHECKER (built into tests/checkers/_mlp_simt.so by __graft_entry__.build(); NOT part of
+// libimmoco_b200.so): fp32 SIMT implementation, the exact-fp32 A/B anchor of the tcgen05 kernels.  A CTA owns tiles of 128 points; the hidden
 // layer is processed in chunks of 64 neurons so the 64-wide motion MLP and the 256-wide image MLP
 // share one code path.  Weights live in shared memory for the whole (persistent) CTA lifetime.
 //
@@ -305,21 +306,13 @@ mlp_bwd_kernel(const float2* __restrict__ enc, const float* __restrict__ w1,
         atomicAdd(g_w1 + (size_t)(c * 64 + 2 * nq + nn) * kIn + 4 * kq + kk, gw1[c][nn * 4 + kk]);
 }
 
-__global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __restrict__ d_post,
-                                float* __restrict__ d_pre, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float t = y[i];
-    d_pre[i] = d_post[i] * (1.0f - t * t);
-  }
-}
-
 template <typename K>
 int resident_ctas(K kernel, int smem_bytes) {
   int per_sm = 1;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  int dev = 0, sms = IMMOCO_NUM_SMS;
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return per_sm * sms;
@@ -352,24 +345,12 @@ int launch_bwd(const float* enc, const float* w1, const float* w2, const float* 
 
 }  // namespace
 
-// implemented in mlp_tc.cu (tcgen05 / TMEM)
-int immoco_mlp_fwd_tc(const float* enc, const float* w1, const float* w2, float* out, int64_t n_points,
-                      int32_t width, int32_t act, int32_t out_tanh, void* stream);
-
-static int g_mlp_impl = 1;   // 1: tcgen05 3xTF32 (product path), 0: fp32 SIMT (A/B check kernels)
-extern "C" int immoco_set_mlp_impl(int32_t impl) {
-  if (impl != 0 && impl != 1) return IMMOCO_ERR_BAD_ARG;
-  g_mlp_impl = impl;
-  return 0;
-}
-extern "C" int immoco_get_mlp_impl(void) { return g_mlp_impl; }
-
-extern "C" int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2, float* out,
-                              int64_t n_points, int32_t width, int32_t act, int32_t out_tanh,
-                              void* stream) {
+// ---- test-side entry points (same contracts as immoco_mlp_fwd / immoco_mlp_bwd of the product library) ----
+extern "C" int immoco_simt_mlp_fwd(const float* enc, const float* w1, const float* w2, float* out,
+                                   int64_t n_points, int32_t width, int32_t act, int32_t out_tanh,
+                                   void* stream) {
   if (n_points < 0 || n_points > 0x3fffffff) return IMMOCO_ERR_BAD_ARG;
   if (n_points == 0) return 0;
-  if (g_mlp_impl == 1) return immoco_mlp_fwd_tc(enc, w1, w2, out, n_points, width, act, out_tanh, stream);
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)n_points;
   if (width == 256 && act == IMMOCO_ACT_RELU) return launch_fwd<256, IMMOCO_ACT_RELU>(enc, w1, w2, out, n, out_tanh, s);
@@ -379,15 +360,11 @@ extern "C" int immoco_mlp_fwd(const float* enc, const float* w1, const float* w2
   return IMMOCO_ERR_UNSUPPORTED;
 }
 
-int immoco_mlp_bwd_tc(const float* enc, const float* w1, const float* w2, const float* d_out, float* d_enc,
-                      float* g_w1, float* g_w2, int64_t n_points, int32_t width, int32_t act, void* stream);
-
-extern "C" int immoco_mlp_bwd(const float* enc, const float* w1, const float* w2, const float* d_out,
-                              float* d_enc, float* g_w1, float* g_w2, int64_t n_points,
-                              int32_t width, int32_t act, void* stream) {
+extern "C" int immoco_simt_mlp_bwd(const float* enc, const float* w1, const float* w2, const float* d_out,
+                                   float* d_enc, float* g_w1, float* g_w2, int64_t n_points,
+                                   int32_t width, int32_t act, void* stream) {
   if (n_points < 0 || n_points > 0x3fffffff) return IMMOCO_ERR_BAD_ARG;
   if (n_points == 0) return 0;
-  if (g_mlp_impl == 1) return immoco_mlp_bwd_tc(enc, w1, w2, d_out, d_enc, g_w1, g_w2, n_points, width, act, stream);
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)n_points;
   if (width == 256 && act == IMMOCO_ACT_RELU) return launch_bwd<256, IMMOCO_ACT_RELU>(enc, w1, w2, d_out, d_enc, g_w1, g_w2, n, s);
@@ -395,14 +372,4 @@ extern "C" int immoco_mlp_bwd(const float* enc, const float* w1, const float* w2
   if (width == 64 && act == IMMOCO_ACT_RELU) return launch_bwd<64, IMMOCO_ACT_RELU>(enc, w1, w2, d_out, d_enc, g_w1, g_w2, n, s);
   if (width == 64 && act == IMMOCO_ACT_TANH) return launch_bwd<64, IMMOCO_ACT_TANH>(enc, w1, w2, d_out, d_enc, g_w1, g_w2, n, s);
   return IMMOCO_ERR_UNSUPPORTED;
-}
-
-extern "C" int immoco_tanh_bwd(const float* y, const float* d_post, float* d_pre, int64_t n, void* stream) {
-  if (n < 0) return IMMOCO_ERR_BAD_ARG;
-  if (n == 0) return 0;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > IMMOCO_NUM_SMS * 8) blocks = IMMOCO_NUM_SMS * 8;
-  tanh_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, d_post, d_pre, n);
-  IMMOCO_LAUNCH_CHECK();
-  return 0;
 }

@@ -72,18 +72,30 @@ def test_hashgrid_forward_and_backward(native_lib, dims, kind, hashgrid_impl):
     assert bool((grad[untouched] == 0).all())
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "simt"])
+class _SimtChecker:
+    """tests/checkers/_mlp_simt.so: the fp32 SIMT MLP kernels, a test-side library with the product entry
+    points' contracts (the product library itself only contains the tcgen05 kernels)."""
+
+    def __init__(self):
+        import __graft_entry__ as entry
+        h = C.CDLL(entry.build_checkers())
+        _P = C.c_void_p
+        h.immoco_simt_mlp_fwd.restype = C.c_int
+        h.immoco_simt_mlp_fwd.argtypes = [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]
+        h.immoco_simt_mlp_bwd.restype = C.c_int
+        h.immoco_simt_mlp_bwd.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]
+        self.immoco_mlp_fwd = h.immoco_simt_mlp_fwd
+        self.immoco_mlp_bwd = h.immoco_simt_mlp_bwd
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "simt-checker"])
 @pytest.mark.parametrize("width,act", [(256, "relu"), (64, "tanh"), (64, "relu"), (256, "tanh")])
 @pytest.mark.parametrize("n", [1, 127, 128, 1000, 40000])
 def test_mlp_forward_and_backward(native_lib, width, act, n, impl):
-    """impl 1 = tcgen05 kind::tf32 with the 3xTF32 split (product path), 0 = fp32 SIMT check kernels;
-    both must meet the same fp32 tolerances against torch fp32."""
-    assert native_lib.immoco_get_mlp_impl() == 1          # the product default is the tensor-core path
-    native_lib.immoco_set_mlp_impl(impl)
-    try:
-        _mlp_case(native_lib, width, act, n)
-    finally:
-        native_lib.immoco_set_mlp_impl(1)
+    """impl 1 = tcgen05 kind::tf32 with the 3xTF32 split (the product library), 0 = the fp32 SIMT check kernels of
+    the test-side library; both must meet the same fp32 tolerances against torch fp32."""
+    assert not hasattr(native_lib, "immoco_set_mlp_impl")      # the product library has no SIMT MLP any more
+    _mlp_case(native_lib if impl == 1 else _SimtChecker(), width, act, n)
 
 
 def _mlp_case(native_lib, width, act, n):
@@ -224,7 +236,6 @@ def test_tensor_core_mlp_is_run_to_run_deterministic(native_lib, width, act, n):
     mbarriers only; a missing dependency would show as run-to-run differences.  d_enc and the forward output
     involve no atomics, so they must be BIT-identical over many launches (the weight gradients are summed
     across CTAs with atomics and may differ in the last bits)."""
-    native_lib.immoco_set_mlp_impl(1)
     a = {"relu": nat.ACT_RELU, "tanh": nat.ACT_TANH}[act]
     g = torch.Generator(device=DEV).manual_seed(n)
     enc = torch.randn(16, n, 2, device=DEV, generator=g) * 3e-2
@@ -285,3 +296,173 @@ def test_hashgrid_row_swizzle_equals_reference_layout(native_lib):
         finally:
             native_lib.immoco_set_hashgrid_impl(1)
         assert float((enc - res["ref"][0]).norm() / res["ref"][0].norm()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------
+# deterministic building blocks (include/immoco_b200.h sections 1b, 2, 7)
+# ------------------------------------------------------------------------------------------------------------
+def _build_csr(native_lib, gs, desc, x):
+    from miccai24_immoco_b200.immoco import GridCsr
+    return GridCsr(gs, desc, x)
+
+
+@pytest.mark.parametrize("dims,kind", [(2, "grid"), (3, "grid"), (2, "ragged"), (3, "ragged"), (3, "tiny"), (2, "small"),
+                                       (3, "small")])
+def test_hashgrid_csr_structure_and_gather_backward(native_lib, dims, kind):
+    """The row-sorted tap list equals the oracle's taps (same rows, same (point, corner) order within a row,
+    same weights bit for bit); the gather backward equals autograd of the oracle encoding and is bit-identical
+    run to run; rows nobody touches are not written."""
+    gs = grid_spec(dims, mb.encoding_config)
+    lv = orc.make_grid_levels(dims, orc.ENCODING_CONFIG)
+    if kind == "small":
+        x = (orc.identity_grid(48, 40).view(-1, 2) if dims == 2 else orc.make_grids((2, 48, 40))).contiguous().to(DEV)
+    else:
+        x = _coords(dims, kind).to(DEV)
+    n = x.shape[0]
+    d = gs.desc()
+    csr = _build_csr(native_lib, gs, d, x)
+    torch.cuda.synchronize()
+    row_ptr = csr.row_ptr.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    taps = csr.taps.cpu().numpy()
+    c = 1 << dims
+    assert row_ptr[0] == 0 and row_ptr[-1] == n * c * 16 and np.all(np.diff(row_ptr) >= 0)
+    if n <= 4000:        # full structural check against the oracle's taps
+        idx, w = orc.all_taps(x.cpu(), lv)                       # (L, C, N)
+        idx, w = idx.numpy(), w.numpy()
+        rows = np.repeat(np.arange(gs.n_rows), np.diff(row_ptr))
+        pts = taps[:, 0].astype(np.int64)
+        wts = taps[:, 1].view(np.float32)
+        for level in range(16):
+            sl = slice(level * n * c, (level + 1) * n * c)
+            # oracle taps of the level ordered by (row, point, corner)
+            o_rows = idx[level].T.reshape(-1)                    # point-major, corner-minor
+            o_pts = np.repeat(np.arange(n), c)
+            o_w = w[level].T.reshape(-1)
+            order = np.lexsort((np.arange(n * c), o_rows))
+            assert np.array_equal(rows[sl], o_rows[order])
+            assert np.array_equal(pts[sl], o_pts[order])
+            assert np.allclose(wts[sl], o_w[order], rtol=0, atol=1e-7)
+    # gather backward vs autograd of the oracle
+    g = torch.Generator().manual_seed(3)
+    table = ((torch.rand(gs.n_rows, 2, generator=g) * 2 - 1) * 1e-1).to(DEV).requires_grad_(True)
+    d_enc = torch.randn(16, n, 2, generator=torch.Generator().manual_seed(4)).to(DEV)
+    ref = orc.hashgrid_encode(x, table, lv, cache=False)
+    (ref * d_enc.permute(1, 0, 2).reshape(n, 32)).sum().backward()
+    cs = csr.struct()
+    grads = []
+    for _ in range(3):
+        grad = torch.full_like(table, 7.0)        # sentinel: untouched rows must keep it
+        nat.check(native_lib.immoco_hashgrid_bwd_csr(C.byref(d), C.byref(cs), d_enc.data_ptr(), grad.data_ptr(), _s()), "bwd_csr")
+        grads.append(grad)
+    touched = torch.from_numpy(np.diff(row_ptr) > 0).to(DEV)
+    assert bool((grads[0][~touched] == 7.0).all())
+    assert bool((table.grad[~touched] == 0).all())
+    assert rel_l2(grads[0][touched], table.grad[touched]) < 2e-6
+    assert torch.equal(grads[1], grads[0]) and torch.equal(grads[2], grads[0])
+    # the atomic scatter gives the same values up to summation order
+    grad_a = torch.zeros_like(table)
+    nat.check(native_lib.immoco_hashgrid_bwd(C.byref(d), x.data_ptr(), d_enc.data_ptr(), grad_a.data_ptr(), n, _s()), "bwd")
+    assert rel_l2(grads[0][touched], grad_a[touched]) < 2e-6
+
+
+def test_hashgrid_csr_honours_row_swizzle(native_lib):
+    gs = grid_spec(3, mb.encoding_config)
+    coords = mb.make_grids((4, 64, 48), "cuda").contiguous()
+    swz = gs.row_swizzle(np.linspace(-1, 1, 4, dtype=np.float32))
+    assert any(swz)
+    perm = torch.from_numpy(gs.row_permutation(swz)).cuda()
+    d_enc = torch.randn(16, coords.shape[0], 2, generator=torch.Generator().manual_seed(1)).cuda()
+    out = {}
+    for name, desc in (("ref", gs.desc()), ("swz", gs.desc(swz))):
+        csr = _build_csr(native_lib, gs, desc, coords)
+        cs = csr.struct()
+        grad = torch.zeros(gs.n_rows, 2, device="cuda")
+        nat.check(native_lib.immoco_hashgrid_bwd_csr(C.byref(desc), C.byref(cs), d_enc.data_ptr(), grad.data_ptr(), _s()), "csr")
+        out[name] = grad
+    # same taps per logical row in the same order -> bit-identical after un-permuting
+    assert torch.equal(out["swz"][perm], out["ref"])
+
+
+def test_hashgrid_csr_fused_adam_equals_gather_then_adam(native_lib):
+    """Gather + Adam in one kernel == gather, then immoco_adam_step on the table, bit for bit, over several
+    steps; rows nobody touches never move."""
+    gs = grid_spec(3, mb.encoding_config)
+    x = mb.make_grids((2, 48, 40), "cuda").contiguous()
+    d = gs.desc()
+    csr = _build_csr(native_lib, gs, d, x)
+    cs = csr.struct()
+    g = torch.Generator().manual_seed(5)
+    p0 = ((torch.rand(gs.n_rows, 2, generator=g) * 2 - 1) * 1e-4).cuda()
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pb, mb_, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    grad = torch.zeros_like(p0)
+    for step in range(1, 5):
+        d_enc = (torch.randn(16, x.shape[0], 2, generator=g) * 10.0 ** float(step - 3)).cuda()
+        nat.check(native_lib.immoco_hashgrid_bwd_csr_adam(C.byref(d), C.byref(cs), d_enc.data_ptr(), pa.data_ptr(),
+                                                          ma.data_ptr(), va.data_ptr(), None, 1e-2, 0.9, 0.999, 1e-8,
+                                                          step, _s()), "csr_adam")
+        nat.check(native_lib.immoco_hashgrid_bwd_csr(C.byref(d), C.byref(cs), d_enc.data_ptr(), grad.data_ptr(), _s()), "csr")
+        nat.check(native_lib.immoco_adam_step(pb.data_ptr(), grad.data_ptr(), mb_.data_ptr(), vb.data_ptr(), pb.numel(),
+                                              1e-2, 0.9, 0.999, 1e-8, step, 0, _s()), "adam")
+        assert torch.equal(pa, pb) and torch.equal(ma, mb_) and torch.equal(va, vb), step
+    row_ptr = csr.row_ptr.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    untouched = torch.from_numpy(np.diff(row_ptr) == 0).cuda()
+    assert int(untouched.sum()) > 0 and torch.equal(pa[untouched], p0[untouched])
+
+
+@pytest.mark.parametrize("width,act,n", [(64, "tanh", 409600), (256, "relu", 102400), (64, "tanh", 1000), (256, "relu", 77)])
+def test_mlp_backward_partials_are_deterministic_and_sum_to_the_gradient(native_lib, width, act, n):
+    """Per-CTA weight-gradient blocks: bit-identical over launches, their ordered sum equals the atomically
+    accumulated gradient (and torch's), d_enc is the same tensor as in the atomic mode; Adam over the blocks
+    equals Adam over their sum."""
+    a = {"relu": nat.ACT_RELU, "tanh": nat.ACT_TANH}[act]
+    g = torch.Generator(device=DEV).manual_seed(n + width)
+    enc = torch.randn(16, n, 2, device=DEV, generator=g) * 0.3
+    w = torch.randn(width * 32 + 16 * width, device=DEV, generator=g) * 0.2
+    w1, w2 = w[: width * 32], w[width * 32:]
+    d_out = torch.randn(n, 2, device=DEV, generator=g)
+    n_mlp = w.numel()
+    n_part = native_lib.immoco_mlp_bwd_partial_count(n)
+    assert 1 <= n_part <= torch.cuda.get_device_properties(0).multi_processor_count
+    parts, d_encs = [], []
+    for _ in range(4):
+        part = torch.zeros(n_part, n_mlp, device=DEV)
+        d_enc = torch.empty_like(enc)
+        nat.check(native_lib.immoco_mlp_bwd_partials(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(),
+                                                     d_enc.data_ptr(), part.data_ptr(), n, width, a, _s()), "partials")
+        parts.append(part)
+        d_encs.append(d_enc)
+    for k in range(1, 4):
+        assert torch.equal(parts[k], parts[0]) and torch.equal(d_encs[k], d_encs[0])
+    g_at = torch.zeros(n_mlp, device=DEV)
+    d_enc_at = torch.empty_like(enc)
+    nat.check(native_lib.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc_at.data_ptr(),
+                                        g_at.data_ptr(), g_at.data_ptr() + 4 * width * 32, n, width, a, _s()), "bwd")
+    assert torch.equal(d_enc_at, d_encs[0])
+    g_sum = parts[0].double().sum(0).float()
+    assert rel_l2(g_sum[: width * 32], g_at[: width * 32]) < 2e-6
+    assert rel_l2(g_sum[width * 32: width * 34], g_at[width * 32: width * 34]) < 2e-6
+    assert bool((parts[0][:, width * 34:] == 0).all())               # padded W2 rows are never written
+    # Adam over the blocks (ordered sum inside the kernel) vs Adam over the fp32 ordered sum
+    g_ord = torch.zeros(n_mlp, device=DEV)
+    for c in range(n_part):
+        g_ord += parts[0][c]
+    pa, ma, va = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    pb, mb_, vb = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    nat.check(native_lib.immoco_adam_step_partials(pa.data_ptr(), parts[0].data_ptr(), n_part, ma.data_ptr(), va.data_ptr(),
+                                                   n_mlp, 1e-2, 0.9, 0.999, 1e-8, 1, _s()), "adam_partials")
+    nat.check(native_lib.immoco_adam_step(pb.data_ptr(), g_ord.data_ptr(), mb_.data_ptr(), vb.data_ptr(), n_mlp, 1e-2, 0.9,
+                                          0.999, 1e-8, 1, 0, _s()), "adam")
+    assert torch.equal(pa, pb) and torch.equal(ma, mb_) and torch.equal(va, vb)
+
+
+def test_release_streams(native_lib):
+    """The library's only hidden state -- one auxiliary stream set per caller stream -- is freed on request."""
+    case = orc.make_case(32, 32, 1, 6)
+    mb.imcoco_motion_correction(case["kspace_motion"], case["masks"], 10)
+    torch.cuda.synchronize()
+    assert native_lib.immoco_release_streams() >= 1
+    assert native_lib.immoco_release_streams() == 0
+    im, _ = mb.imcoco_motion_correction(case["kspace_motion"], case["masks"], 10)      # re-created on demand
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(torch.view_as_real(im)).all())

@@ -19,16 +19,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_loads_and_exports_every_declared_symbol(native_lib):
     header = open(os.path.join(ROOT, "include", "immoco_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|void|immoco_profile\*)\s+(immoco_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|void|immoco_profile\*)\s+(immoco_\w+)\s*\(", header, flags=re.M))
     assert declared, "no declarations parsed"
     assert declared == set(nat.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(native_lib, name) is not None
-    assert native_lib.immoco_abi_version() == 1
+    assert native_lib.immoco_abi_version() == 2
     assert native_lib.immoco_launches_per_iteration(4) == 16 and len(nat.PROFILE_SLOTS) == 16
-    sizes = (C.c_int32 * 3)()
+    assert native_lib.immoco_launches_per_iteration_mode(4, 1, 0) == 17
+    assert native_lib.immoco_launches_per_iteration_mode(4, 1, 1) == 15
+    assert native_lib.immoco_launches_per_iteration_mode(0, 1, 1) == 10
+    sizes = (C.c_int32 * 4)()
     native_lib.immoco_struct_sizes(sizes)
-    assert tuple(sizes) == (C.sizeof(nat.GridDesc), C.sizeof(nat.Lines), C.sizeof(nat.Fit))
+    assert tuple(sizes) == (C.sizeof(nat.GridDesc), C.sizeof(nat.Lines), C.sizeof(nat.Fit), C.sizeof(nat.GridCsr))
+    # the fp32 SIMT MLP kernels are test-side only (tests/checkers), not in the product library
+    assert not hasattr(native_lib, "immoco_set_mlp_impl") and "mlp.cu" not in nat.SOURCES
+    assert native_lib.immoco_get_deterministic() in (0, 1)
 
 
 def test_library_targets_sm100a():
