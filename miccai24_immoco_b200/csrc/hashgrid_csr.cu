@@ -89,12 +89,24 @@ struct AdamConsts {
   float omb1, b2, omb2, step_size, bc2_sqrt, eps;
 };
 
+// parameter / moment loads of a row are issued BEFORE its gather loop (ADAM) so that they overlap it
+struct RowState {
+  float2 p, m, v;
+};
 template <bool ADAM>
-__device__ __forceinline__ void finish_row(uint32_t row, float gx, float gy, float2* __restrict__ grad,
-                                           float2* __restrict__ table, float2* __restrict__ m,
-                                           float2* __restrict__ v, const AdamConsts& a) {
+__device__ __forceinline__ RowState load_row_state(uint32_t row, const float2* __restrict__ table,
+                                                   const float2* __restrict__ m, const float2* __restrict__ v) {
+  RowState st;
+  if (ADAM) { st.p = table[row]; st.m = m[row]; st.v = v[row]; }
+  return st;
+}
+
+template <bool ADAM>
+__device__ __forceinline__ void finish_row(uint32_t row, float gx, float gy, const RowState& st,
+                                           float2* __restrict__ grad, float2* __restrict__ table,
+                                           float2* __restrict__ m, float2* __restrict__ v, const AdamConsts& a) {
   if (ADAM) {
-    float2 p = table[row], mm = m[row], vv = v[row];
+    float2 p = st.p, mm = st.m, vv = st.v;
     adam_update(p.x, mm.x, vv.x, gx, a.omb1, a.b2, a.omb2, a.step_size, a.bc2_sqrt, a.eps);
     adam_update(p.y, mm.y, vv.y, gy, a.omb1, a.b2, a.omb2, a.step_size, a.bc2_sqrt, a.eps);
     table[row] = p;
@@ -107,8 +119,8 @@ __device__ __forceinline__ void finish_row(uint32_t row, float gx, float gy, flo
 }
 
 // taps per thread and trip of the narrow path: all index records first, then all gathers, then the
-// ordered sum -- 4 independent L2 round trips in flight per thread
-constexpr int kUnroll = 4;
+// ordered sum -- 8 independent L2 round trips in flight per thread (a fine-level row has ~6 taps: one trip)
+constexpr int kUnroll = 8;
 
 template <bool ADAM>
 __global__ void __launch_bounds__(kThreads)
@@ -130,6 +142,8 @@ hashgrid_bwd_gather_kernel(const __grid_constant__ immoco_grid_desc g, const __g
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t s = __ldg(row_ptr + off + r), e = __ldg(row_ptr + off + r + 1);
     if (s == e) return;
+    RowState st;
+    if (lane == 0) st = load_row_state<ADAM>(off + r, table, m, v);
     float ax = 0.f, ay = 0.f;
     for (uint32_t k = s + lane; k < e; k += 64) {       // lane-strided, two taps in flight per lane
       const uint2 t0 = __ldg(taps + k);
@@ -147,12 +161,13 @@ hashgrid_bwd_gather_kernel(const __grid_constant__ immoco_grid_desc g, const __g
       ax += __shfl_xor_sync(0xffffffffu, ax, o);
       ay += __shfl_xor_sync(0xffffffffu, ay, o);
     }
-    if (lane == 0) finish_row<ADAM>(off + r, ax, ay, grad, table, m, v, a);
+    if (lane == 0) finish_row<ADAM>(off + r, ax, ay, st, grad, table, m, v, a);
   } else {
     const uint32_t r = cta * kThreads + threadIdx.x;
     if (r >= entries) return;
     const uint32_t s = __ldg(row_ptr + off + r), e = __ldg(row_ptr + off + r + 1);
     if (s == e) return;
+    const RowState st = load_row_state<ADAM>(off + r, table, m, v);
     float ax = 0.f, ay = 0.f;
     for (uint32_t k = s; k < e; k += kUnroll) {
       uint2 t[kUnroll];
@@ -167,7 +182,7 @@ hashgrid_bwd_gather_kernel(const __grid_constant__ immoco_grid_desc g, const __g
         ay = fmaf(__uint_as_float(t[u].y), d[u].y, ay);
       }
     }
-    finish_row<ADAM>(off + r, ax, ay, grad, table, m, v, a);
+    finish_row<ADAM>(off + r, ax, ay, st, grad, table, m, v, a);
   }
 }
 

@@ -17,7 +17,17 @@ OUT_PAD = 16          # tiny-cuda-nn pads the output layer to 16 rows
 N_ENCODED = 32        # kernels are specialised for 16 levels x 2 features
 
 _KNOWN_ENC_KEYS = {"otype", "type", "n_levels", "n_features_per_level", "log2_hashmap_size",
-                   "base_resolution", "per_level_scale", "interpolation", "fine_resolution"}
+                   "base_resolution", "per_level_scale", "interpolation", "fine_resolution", "stride_wrap"}
+
+# Process-wide default of the ``stride_wrap`` encoding option (see grid_spec); the config key wins.
+_STRIDE_WRAP_DEFAULT = False
+
+
+def set_stride_wrap_default(on: bool) -> None:
+    """tiny-cuda-nn compatibility switch for every grid built afterwards without an explicit
+    ``"stride_wrap"`` key in its encoding config (see ``grid_spec``)."""
+    global _STRIDE_WRAP_DEFAULT
+    _STRIDE_WRAP_DEFAULT = bool(on)
 _ACTS = {"none": nat.ACT_NONE, "relu": nat.ACT_RELU, "tanh": nat.ACT_TANH}
 
 
@@ -101,7 +111,16 @@ class GridSpec:
 
 
 def grid_spec(n_dims: int, cfg: dict) -> GridSpec:
-    """Level scales / resolutions / entry counts / offsets of a Grid-Hash encoding."""
+    """Level scales / resolutions / entry counts / offsets of a Grid-Hash encoding.
+
+    ``cfg["stride_wrap"]`` (default False = SURVEY.md section 8's contract): how grid_index()'s dense-index
+    stride is kept while the level kinds are decided.  False: as a mathematical integer -- with the reference
+    configuration levels 6-15 (2-D) / 3-15 (3-D) are hashed.  True: in a uint32 like tiny-cuda-nn's
+    ``grid_index`` keeps it -- for resolutions >= 2^16 (levels 12-15 here) ``stride * res`` wraps to 0, the
+    hash branch is skipped and those levels index densely with the wrapped strides,
+    (q0 + q1 * res) mod 2^19, the third coordinate dropping out.  The kernels take the per-level kind from the
+    host (``immoco_grid_desc::hashed``) and their dense index arithmetic is uint32 anyway, so both modes run
+    the same code (DESIGN.md Q12; tests/test_gpu_kernels.py::test_hashgrid_stride_wrap_mode)."""
     if n_dims not in (2, 3):
         raise NotImplementedError("the IM-MoCo path uses 2-D and 3-D hash grids only")
     if str(cfg.get("otype", "Grid")) not in ("Grid", "HashGrid") or str(cfg.get("type", "Hash")) != "Hash":
@@ -115,6 +134,7 @@ def grid_spec(n_dims: int, cfg: dict) -> GridSpec:
     log2_t = int(cfg.get("log2_hashmap_size", 19))
     base = int(cfg.get("base_resolution", 16))
     log2_pls = math.log2(float(cfg.get("per_level_scale", 2.0)))
+    wrap = bool(cfg.get("stride_wrap", _STRIDE_WRAP_DEFAULT))
     scales, ress, ents, offs, hashed = [], [], [], [0], []
     for lvl in range(n_levels):
         scale = float(np.float32(np.exp2(np.float32(lvl * log2_pls)) * np.float32(base) - np.float32(1.0)))
@@ -127,6 +147,8 @@ def grid_spec(n_dims: int, cfg: dict) -> GridSpec:
         stride, dim = 1, 0
         while dim < n_dims and stride <= n:
             stride *= res
+            if wrap:
+                stride &= 0xFFFFFFFF
             dim += 1
         scales.append(scale)
         ress.append(res)

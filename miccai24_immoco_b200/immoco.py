@@ -286,7 +286,8 @@ class GridCsr:
 
 
 def _cached_csr(kind: str, shape, grid, swizzle, coords: torch.Tensor) -> GridCsr:
-    key = (kind, tuple(int(v) for v in shape), str(coords.device), grid.n_dims, grid.offsets, tuple(swizzle))
+    key = (kind, tuple(int(v) for v in shape), str(coords.device), grid.n_dims, grid.offsets, grid.hashed,
+           tuple(swizzle))
     csr = _CSR_CACHE.get(key)
     if csr is None:
         csr = GridCsr(grid, grid.desc(swizzle), coords)

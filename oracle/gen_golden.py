@@ -159,9 +159,10 @@ def _inr_forward_via_fp64(self, x):
 
 
 def loop_golden(ref_immoco, tag, h, n_mov, seed, iters, out_dir, check_restatement=True,
-                small_payload=False):
-    """Reference loop (immoco.py:116-206) with injected params on a synthetic square slice."""
-    case = orc.make_case(h, h, n_mov, seed)
+                small_payload=False, w=None):
+    """Reference loop (immoco.py:116-206) with injected params on a synthetic (h, w) slice (square by default)."""
+    w = h if w is None else w
+    case = orc.make_case(h, w, n_mov, seed)
     masks = case["masks"]
     p_img = seeded_params(2, orc.IMAGE_NETWORK_CONFIG, 100 + seed)
     p_mot = seeded_params(3, orc.MOTION_NETWORK_CONFIG, 200 + seed)
@@ -222,7 +223,7 @@ def loop_golden(ref_immoco, tag, h, n_mov, seed, iters, out_dir, check_restateme
     print(f"  {tag}: rounding-drift band: max rel loss diff its<10 {max(rel[:10]):.2e}, "
           f"<{min(50, iters)} {max(rel[:50]):.2e}, all {max(rel):.2e}; perturbed metrics {met_p}")
     payload = dict(
-        h=h, n_mov=n_mov, seed=seed, iters=iters,
+        h=h, w=w, n_mov=n_mov, seed=seed, iters=iters,
         masks_lines=masks[:, 0, :].numpy().astype(np.uint8),
         k_fwd0=k_ref.numpy(),
         loss_trace=np.asarray(trace, dtype=np.float64),
@@ -242,6 +243,9 @@ def main():
     ap.add_argument("--full", action="store_true", help="also the 320x320, n_M=4 case (slow)")
     ap.add_argument("--full-iters", type=int, default=200)
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--c3", action="store_true", help="also a 640x368, n_M=5 case (config 3 shape; slow)")
+    ap.add_argument("--c3-iters", type=int, default=30)
+    ap.add_argument("--c3-seed", type=int, default=1003)
     ap.add_argument("--full-seed", type=int, default=1004,
                     help="slice seed of the 320x320 case (1004: corrupted PSNR 29.6 dB / SSIM 0.953)")
     args = ap.parse_args()
@@ -260,6 +264,10 @@ def main():
         print(f"[loop 320x320, n_M=4, {args.full_iters} its]")
         loop_golden(ref_immoco, f"c2_i{args.full_iters}", 320, 4, seed=args.full_seed, iters=args.full_iters,
                     out_dir=out_dir, check_restatement=False, small_payload=True)
+    if args.c3:
+        print(f"[loop 640x368, n_M=5, {args.c3_iters} its (config 3 shape)]")
+        loop_golden(ref_immoco, f"c3_i{args.c3_iters}", 640, 5, seed=args.c3_seed, iters=args.c3_iters,
+                    out_dir=out_dir, check_restatement=False, small_payload=True, w=368)
     print("done")
 
 

@@ -80,6 +80,7 @@ class GridLevels:
     entries: Tuple[int, ...]         # "hashmap_size" of each level
     offsets: Tuple[int, ...]         # prefix sums, len n_levels+1
     hashed: Tuple[bool, ...]         # informational: does grid_index() take the hash branch?
+    stride_wrap: bool = False        # uint32 stride in grid_index() (tiny-cuda-nn compatibility mode)
 
     @property
     def n_table_params(self) -> int:
@@ -94,7 +95,7 @@ def _u32(v: int) -> int:
     return v & _U32
 
 
-def level_uses_hash(n_dims: int, entries: int, resolution: int) -> bool:
+def level_uses_hash(n_dims: int, entries: int, resolution: int, stride_wrap: bool = False) -> bool:
     """Replays grid_index()'s stride loop for one level [ext]: hash iff the dense index range
     (resolution**dims walked while stride <= entries) exceeds the level's entry count.
 
@@ -102,12 +103,16 @@ def level_uses_hash(n_dims: int, entries: int, resolution: int) -> bool:
     for power-of-two resolutions >= 2**16 the product would wrap to 0 and skip the hash branch.
     SURVEY.md section 8 a1/a2 (the build contract, incl. its touched-entry counts 3.04 M / 6.51 M)
     specifies levels 6-15 (2-D) and 3-15 (3-D) as hashed, i.e. a non-wrapping stride; this
-    oracle and the kernels follow the contract.  See DESIGN.md "Q12".
+    oracle and the kernels follow the contract by default.  ``stride_wrap=True`` selects the uint32
+    behaviour instead (encoding config key "stride_wrap"): the product wraps, the loop runs on with stride
+    0 and the level indexes densely with the wrapped strides.  See DESIGN.md "Q12".
     """
     stride = 1
     dim = 0
     while dim < n_dims and stride <= entries:
         stride = stride * resolution
+        if stride_wrap:
+            stride &= _U32
         dim += 1
     return entries < stride
 
@@ -123,6 +128,7 @@ def make_grid_levels(n_dims: int, cfg: dict) -> GridLevels:
     base = int(cfg.get("base_resolution", 16))
     pls = float(cfg.get("per_level_scale", 2.0))
     log2_pls = math.log2(pls)
+    wrap = bool(cfg.get("stride_wrap", False))
     scales, ress, ents, offs, hashed = [], [], [], [0], []
     for lvl in range(n_levels):
         # grid_scale(): exp2f(level * log2_per_level_scale) * base_resolution - 1.0f
@@ -137,9 +143,9 @@ def make_grid_levels(n_dims: int, cfg: dict) -> GridLevels:
         ress.append(res)
         ents.append(n)
         offs.append(offs[-1] + n)
-        hashed.append(level_uses_hash(n_dims, n, res))
+        hashed.append(level_uses_hash(n_dims, n, res, wrap))
     return GridLevels(n_dims, n_levels, n_feat, tuple(scales), tuple(ress), tuple(ents),
-                      tuple(offs), tuple(hashed))
+                      tuple(offs), tuple(hashed), wrap)
 
 
 def _mul_u32(q: torch.Tensor, c: int) -> torch.Tensor:
@@ -149,7 +155,7 @@ def _mul_u32(q: torch.Tensor, c: int) -> torch.Tensor:
     return (q * lo + (((q * hi) & 0xFFFF) << 16)) & _U32
 
 
-def grid_corner_index(q: Sequence[torch.Tensor], entries: int, res: int) -> torch.Tensor:
+def grid_corner_index(q: Sequence[torch.Tensor], entries: int, res: int, stride_wrap: bool = False) -> torch.Tensor:
     """grid_index<N_DIMS>() of tiny-cuda-nn [ext], uint32 arithmetic emulated in int64."""
     n_dims = len(q)
     stride = 1
@@ -157,7 +163,9 @@ def grid_corner_index(q: Sequence[torch.Tensor], entries: int, res: int) -> torc
     dim = 0
     while dim < n_dims and stride <= entries:
         idx = (idx + _mul_u32(q[dim], stride & _U32)) & _U32
-        stride = stride * res          # not wrapped, see level_uses_hash()
+        stride = stride * res          # not wrapped by default, see level_uses_hash()
+        if stride_wrap:
+            stride &= _U32
         dim += 1
     if entries < stride:
         idx = torch.zeros_like(q[0])
@@ -186,7 +194,7 @@ def hashgrid_taps(x: torch.Tensor, lv: GridLevels, level: int):
             q.append((cell[:, d] + bit) & _U32)
             wd = frac[:, d] if bit else (1.0 - frac[:, d])
             w = wd if w is None else w * wd
-        idxs.append(grid_corner_index(q, ent, res))
+        idxs.append(grid_corner_index(q, ent, res, lv.stride_wrap))
         ws.append(w)
     return torch.stack(idxs), torch.stack(ws)
 

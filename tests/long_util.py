@@ -1,0 +1,70 @@
+"""1000-iteration fits of the headline configuration (C2: 320x320, n_M=4) -- ours against the oracle loop
+run on the same GPU -- shared by tests/test_gpu_long.py (asserts) and tools/long_run_stats.py (the table kept
+under profiles/).
+
+The loop is chaotic: a 1-ulp perturbation of the initial parameters changes the trajectory of
+the ORACLE ITSELF by percents after a few dozen iterations.  A 1000-iteration comparison can therefore only be
+statistical: per slice we record the tail loss (median of the last 50 iterations -- the last sample alone
+sits on or off one of Adam's loss spikes), the final PSNR / SSIM against the ground-truth phantom, and
+compare ours - oracle with oracle(perturbed) - oracle over the same slices."""
+import numpy as np
+import torch
+
+import miccai24_immoco_b200 as mb
+from oracle import immoco_oracle as orc
+from tests.gpu_util import case_params
+
+DEV = "cuda"
+H = W = 320
+N_MOV = 4
+
+
+def summarize(trace, image_abs, gt_abs):
+    trace = np.asarray(trace, dtype=np.float64)
+    met = orc.crop_metrics(image_abs.cpu(), gt_abs)
+    return {"tail": float(np.median(trace[-50:])), "last": float(trace[-1]), "max_tail": float(trace[-50:].max()),
+            "spikes": int((trace[200:] > 10.0 * np.median(trace[-50:])).sum()),
+            "psnr": float(met["psnr"]), "ssim": float(met["ssim"])}
+
+
+def run_ours(seed, iters, deterministic):
+    case = orc.make_case(H, W, N_MOV, seed)
+    p_img, p_mot = case_params(seed, DEV)
+    im, _, trace = mb.imcoco_motion_correction(case["kspace_motion"].to(DEV), case["masks"].to(DEV), iters=iters,
+                                               image_params=p_img, motion_params=p_mot, return_trace=True,
+                                               deterministic=deterministic)
+    return summarize(trace, im.abs(), case["image"].abs())
+
+
+def run_oracle(seed, iters, perturb=0.0):
+    """The oracle loop (torch fp32, TF32 off) on the GPU; ``perturb`` > 0 multiplies the initial image-INR
+    parameters by (1 + perturb * N(0,1)) -- 1e-7 flips the last bit of a fraction of them."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    case = orc.make_case(H, W, N_MOV, seed)
+    p_img, p_mot = case_params(seed, DEV)
+    if perturb > 0:
+        g = torch.Generator(device=DEV).manual_seed(seed)
+        p_img = p_img * (1.0 + perturb * torch.randn(p_img.shape, device=DEV, generator=g))
+    im, _, trace = orc.imcoco_motion_correction(case["kspace_motion"].to(DEV), case["masks"].to(DEV), iters=iters,
+                                                image_params=p_img, motion_params=p_mot, return_trace=True)
+    return summarize(trace, im.detach().abs(), case["image"].abs())
+
+
+def compare(seeds, iters=1000, modes=("deterministic", "atomic"), log=print):
+    rows = []
+    for seed in seeds:
+        row = {"seed": seed, "oracle": run_oracle(seed, iters), "oracle_perturbed": run_oracle(seed, iters, 1e-7)}
+        for mode in modes:
+            row[mode] = run_ours(seed, iters, mode == "deterministic")
+        rows.append(row)
+        log("seed %d: " % seed + "; ".join(
+            "%s tail %.5f last %.5f psnr %.3f ssim %.4f spikes %d" % (k, v["tail"], v["last"], v["psnr"], v["ssim"], v["spikes"])
+            for k, v in row.items() if k != "seed"))
+    return rows
+
+
+def spread(rows, a, b, key, relative=False):
+    """|a - b| per slice for metric `key` (relative to b when asked)."""
+    d = np.asarray([abs(r[a][key] - r[b][key]) / (abs(r[b][key]) if relative else 1.0) for r in rows])
+    return d

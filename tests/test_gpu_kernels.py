@@ -466,3 +466,63 @@ def test_release_streams(native_lib):
     im, _ = mb.imcoco_motion_correction(case["kspace_motion"], case["masks"], 10)      # re-created on demand
     torch.cuda.synchronize()
     assert bool(torch.isfinite(torch.view_as_real(im)).all())
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("kind", ["grid", "ragged"])
+def test_hashgrid_stride_wrap_mode(native_lib, dims, kind):
+    """encoding_config["stride_wrap"] = True: grid_index()'s stride kept in a uint32 like tiny-cuda-nn does --
+    levels 12-15 (resolution >= 2^16) skip the hash and index densely with the wrapped strides.  Same kernels
+    (the level kinds come from the host); forward, atomic backward and gather backward against the oracle."""
+    cfg_o = dict(orc.ENCODING_CONFIG, stride_wrap=True)
+    gs = grid_spec(dims, dict(mb.encoding_config, stride_wrap=True))
+    lv = orc.make_grid_levels(dims, cfg_o)
+    assert gs.hashed[12:] == (0, 0, 0, 0) and grid_spec(dims, mb.encoding_config).hashed[12:] == (1, 1, 1, 1)
+    assert tuple(int(v) for v in lv.hashed) == gs.hashed
+    x = _coords(dims, kind).to(DEV)
+    n = x.shape[0]
+    g = torch.Generator().manual_seed(3)
+    table = ((torch.rand(gs.n_rows, 2, generator=g) * 2 - 1) * 1e-1).to(DEV).requires_grad_(True)
+    enc = torch.empty((16, n, 2), device=DEV)
+    d = gs.desc()
+    nat.check(native_lib.immoco_hashgrid_fwd(C.byref(d), x.data_ptr(), table.data_ptr(), enc.data_ptr(), n, _s()), "fwd")
+    ref = orc.hashgrid_encode(x, table, lv, cache=False)
+    got = enc.permute(1, 0, 2).reshape(n, 32)
+    assert rel_l2(got, ref) < 1e-6
+    # the two modes really differ on the finest levels
+    lv0 = orc.make_grid_levels(dims, orc.ENCODING_CONFIG)
+    ref0 = orc.hashgrid_encode(x, table, lv0, cache=False)
+    assert rel_l2(ref[:, 24:], ref0[:, 24:]) > 1e-2 and torch.equal(ref[:, :24], ref0[:, :24])
+    d_enc = torch.randn(16, n, 2, generator=torch.Generator().manual_seed(4)).to(DEV)
+    (ref * d_enc.permute(1, 0, 2).reshape(n, 32)).sum().backward()
+    grad = torch.zeros_like(table)
+    nat.check(native_lib.immoco_hashgrid_bwd(C.byref(d), x.data_ptr(), d_enc.data_ptr(), grad.data_ptr(), n, _s()), "bwd")
+    assert rel_l2(grad, table.grad) < 2e-6
+    csr = _build_csr(native_lib, gs, d, x)
+    cs = csr.struct()
+    grad_c = torch.zeros_like(table)
+    nat.check(native_lib.immoco_hashgrid_bwd_csr(C.byref(d), C.byref(cs), d_enc.data_ptr(), grad_c.data_ptr(), _s()), "csr")
+    assert rel_l2(grad_c, table.grad) < 2e-6
+
+
+def test_fit_in_stride_wrap_mode_matches_oracle():
+    """A short fit with the tiny-cuda-nn-compatible level kinds on both sides (oracle config key / package default)."""
+    from miccai24_immoco_b200 import encoding as enc_mod
+    h, w, n_mov, seed, iters = 64, 48, 2, 3, 12
+    case = orc.make_case(h, w, n_mov, seed)
+    p_img, p_mot = case_params(seed)
+    saved = dict(orc.ENCODING_CONFIG)
+    try:
+        enc_mod.set_stride_wrap_default(True)
+        orc.ENCODING_CONFIG["stride_wrap"] = True
+        _, _, trace = mb.imcoco_motion_correction(case["kspace_motion"].to(DEV), case["masks"].to(DEV), iters=iters,
+                                                  image_params=p_img.to(DEV), motion_params=p_mot.to(DEV),
+                                                  return_trace=True, deterministic=True)
+        _, _, trace_o = orc.imcoco_motion_correction(case["kspace_motion"], case["masks"], iters=iters,
+                                                     image_params=p_img, motion_params=p_mot, return_trace=True)
+    finally:
+        enc_mod.set_stride_wrap_default(False)
+        orc.ENCODING_CONFIG.clear()
+        orc.ENCODING_CONFIG.update(saved)
+    rel = np.abs(trace - np.asarray(trace_o)) / np.abs(trace_o)
+    assert rel[0] < 1e-5 and rel.max() < 1e-3, rel

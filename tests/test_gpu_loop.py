@@ -184,8 +184,9 @@ def test_engine_equals_module_mode_for_three_steps():
 
 def _run_golden(golden, iters=None):
     h, n_mov, seed = int(golden["h"]), int(golden["n_mov"]), int(golden["seed"])
+    w = int(golden["w"]) if "w" in golden.files else h
     iters = int(golden["iters"]) if iters is None else iters
-    case = orc.make_case(h, h, n_mov, seed)
+    case = orc.make_case(h, w, n_mov, seed)
     assert np.array_equal(case["masks"][:, 0, :].numpy().astype(np.uint8), golden["masks_lines"])
     p_img, p_mot = case_params(seed, DEV)
     im, k, trace = mb.imcoco_motion_correction(case["kspace_motion"].to(DEV), case["masks"].to(DEV),
@@ -249,6 +250,25 @@ def test_loop_c2_against_reference_golden(golden_dir):
         return ok, (d_psnr, band_psnr, d_ssim, band_ssim)
 
     _golden_once(g, 50, final_check)
+
+
+def test_loop_c3_shape_against_reference_golden(golden_dir):
+    """Config 3's shape (640x368, n_M=5): loss trace of the reference's own loop (oracle/gen_golden.py --c3),
+    strict forward parity at iteration 0 and the drift-band rule afterwards."""
+    path = os.path.join(golden_dir, "loop_c3_i30.npz")
+    if not os.path.exists(path):
+        pytest.skip("640x368 golden not generated")
+    g = np.load(path)
+    case, im, k, trace = _golden_once(g, int(g["iters"]))
+    assert im.shape == (640, 368) and trace.shape[0] == int(g["iters"])
+    # iteration-0 forward vs the REFERENCE's forward
+    p_img, p_mot = case_params(int(g["seed"]), DEV)
+    ours = mb.IMMoCo(case["masks"].to(DEV))
+    with torch.no_grad():
+        ours.image_inr.params.copy_(p_img)
+        ours.motion_inr.params.copy_(p_mot)
+        k0, _ = ours()
+    assert rel_l2(k0, torch.from_numpy(g["k_fwd0"])) < 1e-4
 
 
 def test_forward_kspace_against_reference_golden_c2(golden_dir):

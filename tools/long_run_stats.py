@@ -1,0 +1,33 @@
+"""1000-iteration C2 fits, ours (deterministic + atomic) vs the oracle loop on the same GPU (+ its 1-ulp
+perturbed self), per slice: tail loss, last loss, loss spikes, final PSNR / SSIM.  The table is kept under
+profiles/ (round2_long_runs.txt).   python tools/long_run_stats.py [--seeds 8] [--iters 1000]"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import miccai24_immoco_b200 as mb  # noqa: E402
+from tests import long_util as lu  # noqa: E402
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=1000)
+    a = ap.parse_args()
+    mb.build()
+    t0 = time.time()
+    rows = lu.compare(range(1000, 1000 + a.seeds), iters=a.iters, log=lambda s: print(s, flush=True))
+    print(f"[{time.time() - t0:.0f} s]")
+    for mode in ("deterministic", "atomic", "oracle_perturbed"):
+        for key, rel in (("psnr", False), ("ssim", False), ("tail", True), ("last", True)):
+            d = lu.spread(rows, mode, "oracle", key, rel)
+            print(f"{mode:17s} vs oracle, {key:4s}{' (relative)' if rel else ''}: median {np.median(d):.4g}  max {d.max():.4g}")
+    for name in ("oracle", "oracle_perturbed", "deterministic", "atomic"):
+        last = np.asarray([r[name]["last"] for r in rows])
+        tail = np.asarray([r[name]["tail"] for r in rows])
+        print(f"{name:17s}: last-iteration loss min {last.min():.5f} max {last.max():.5f}; tail median min {tail.min():.5f} "
+              f"max {tail.max():.5f}; runs whose last sample is > 10 x their tail median: {(last > 10 * tail).sum()} of {len(rows)}; "
+              f"loss spikes after it 200 (> 10 x tail): {[r[name]['spikes'] for r in rows]}")
