@@ -264,6 +264,16 @@ int immoco_set_profile_overlap(int32_t on);
 int immoco_fit_run(const immoco_fit* fit, int32_t it_begin, int32_t it_end,
                    const float* lambdas_host, void* stream, immoco_profile* prof,
                    int32_t profile_every);
+/* The same loop over a BATCH of n_fits (<= immoco_max_fit_batch()) independent fits of ONE shape (h, w, m,
+ * network widths, grid layouts, accumulation mode), advanced in lock step with the same lambda schedule: the
+ * latency-bound kernels of an iteration (row / column passes, gradient entropy, MLP forward) are issued once
+ * for all instances (grid z / y = instance), the kernels that fill the GPU alone (hash grid, MLP backward,
+ * Adam) per instance.  Each instance gets exactly the result of its own immoco_fit_run (bit for bit in
+ * deterministic mode).  This is "within a GPU, batch B instances" of src/test/test_immoco.py:45-72's loop. */
+int immoco_fit_run_batched(const immoco_fit* const* fits, int32_t n_fits, int32_t it_begin, int32_t it_end,
+                           const float* lambdas_host, void* stream, immoco_profile* prof,
+                           int32_t profile_every);
+int immoco_max_fit_batch(void);
 /* 1 (default): the image-INR branch of every non-instrumented iteration runs on an internal
  * auxiliary stream, forked from / joined to `stream` with events; 0: everything on `stream`. */
 int immoco_set_branch_overlap(int32_t on);

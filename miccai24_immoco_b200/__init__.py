@@ -11,9 +11,9 @@ Every compute call goes to hand-written sm_100a kernels in libimmoco_b200.so thr
 include/immoco_b200.h; there is no CPU or eager-PyTorch fallback.
 """
 from ._native import build, lib, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
-from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, encoding_config,  # noqa: F401
+from .immoco import (ClearCache, FitEngine, IMMoCo, LineStructure, clear_caches, encoding_config,  # noqa: F401
                      imcoco_motion_correction, lambda_schedule, make_grids, mot_network_config,
-                     network_config)
+                     network_config, run_batched)
 from .autofocusing import Autofocusing, autofocus_motion_correction  # noqa: F401
 from .batch import reconstruct_batch  # noqa: F401
 from .kld_net import Unet, detect_motion_lines, get_unet, kld_net_input, movement_masks_from_kspace  # noqa: F401
@@ -27,7 +27,7 @@ __all__ = [
     "imcoco_motion_correction", "IMMoCo", "make_grids", "network_config", "mot_network_config",
     "encoding_config", "ClearCache", "NetworkWithInputEncoding", "FFT", "IFFT",
     "GradientEntropyLoss", "extract_movement_groups", "lines_from_mask", "FitEngine",
-    "LineStructure", "lambda_schedule", "build", "lib", "reconstruct_batch", "reconstruct_slices",
+    "LineStructure", "lambda_schedule", "run_batched", "clear_caches", "build", "lib", "reconstruct_batch", "reconstruct_slices",
     "gather_images", "shard_indices", "calmetric2D", "crop_metrics", "my_psnr", "normalize", "rmse",
     "Autofocusing", "autofocus_motion_correction", "get_unet", "Unet", "kld_net_input", "detect_motion_lines", "movement_masks_from_kspace",
     "motion_simulation2D", "generate_list", "get_rand_int", "rotation_matrix_2d",

@@ -126,6 +126,9 @@ _SIGNATURES = {
                                    C.c_double, C.c_int32, C.c_int32, _P]),
     "immoco_fit_run": (C.c_int, [C.POINTER(Fit), C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P,
                                  C.c_int32]),
+    "immoco_fit_run_batched": (C.c_int, [C.POINTER(C.POINTER(Fit)), C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_float), _P, _P, C.c_int32]),
+    "immoco_max_fit_batch": (C.c_int, []),
     "immoco_metrics2d": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "immoco_rigid_resample": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),

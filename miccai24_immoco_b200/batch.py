@@ -24,19 +24,22 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .immoco import FitEngine, IMMoCo, lambda_schedule
+from .immoco import FitEngine, IMMoCo, lambda_schedule, run_batched
 
 DEFAULT_IN_FLIGHT = 1
 DEFAULT_CHUNK = 10
+# slices of one shape fitted in lock step by immoco_fit_run_batched (the latency-bound kernels of an iteration
+# are one launch for all of them); measured on B200 in profiles/round2_batched_fit.txt
+DEFAULT_BATCH = 4
 
 
 class _Slot:
     def __init__(self, device):
         self.stream = torch.cuda.Stream(device=device)
-        self.index = -1          # slice being fitted, -1: idle
-        self.done = 0            # iterations issued
-        self.model = None
-        self.engine = None
+        self.indices: List[int] = []     # slices being fitted in lock step, empty: idle
+        self.done = 0                    # iterations issued
+        self.models: list = []
+        self.engines: list = []
 
 
 def _as_pinned(t: torch.Tensor) -> torch.Tensor:
@@ -52,14 +55,16 @@ def reconstruct_batch(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Ten
                       motion_params: Optional[Sequence[torch.Tensor]] = None,
                       seeds: Optional[Sequence[int]] = None, kmax: float = 16000.0, variant: str = "main",
                       return_kspace: bool = False, return_traces: bool = False, device=None,
-                      deterministic: Optional[bool] = None):
+                      deterministic: Optional[bool] = None, batch: int = DEFAULT_BATCH):
     """``imcoco_motion_correction`` over a stack of slices, ``in_flight`` of them concurrently.
 
     kspaces[i]: (H, W) complex k-space, masks[i]: (M_i, H, W) movement-group masks (host or device;
     host tensors are uploaded stream-ordered).  Slices may differ in shape and in M.  Returns the list
     of corrected images (complex64 CUDA tensors, 16000-normalised scale); with
     ``return_kspace`` / ``return_traces`` a tuple (images, kspaces_fwd, traces) with None for the parts
-    not asked for.  Loss traces are read back once at the end.
+    not asked for.  Loss traces are read back once at the end.  ``batch``: up to this many pending slices of
+    the SAME shape and movement-group count are fitted in lock step through ``immoco_fit_run_batched`` (each
+    slice still gets exactly the result of its own fit).
     """
     if not torch.cuda.is_available():
         raise RuntimeError("reconstruct_batch needs a CUDA device (no CPU fallback)")
@@ -76,9 +81,12 @@ def reconstruct_batch(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Ten
     images: List[Optional[torch.Tensor]] = [None] * n
     ksp_out: List[Optional[torch.Tensor]] = [None] * n
     losses: List[Optional[torch.Tensor]] = [None] * n
-    chunk = max(1, int(chunk))
+    chunk = max(1, int(chunk)) if len(slots) > 1 else max(1, iters)     # one slot: nothing to interleave with
 
-    def start(slot: _Slot, i: int) -> None:
+    def shape_key(i: int):
+        return (tuple(kspaces[i].shape[-2:]), int(masks[i].shape[0]))
+
+    def start_one(i: int):
         m_in = masks[i]
         k_in = kspaces[i]
         host_masks = None if m_in.is_cuda else m_in
@@ -94,34 +102,50 @@ def reconstruct_batch(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Ten
         scale = k_dev.abs().max()                      # stays on the device (immoco.py:137-139)
         engine = FitEngine(model, max(iters, 1), deterministic=deterministic)
         engine.set_kspace(k_dev.div(scale).mul(kmax))
-        slot.index, slot.done, slot.model, slot.engine = i, 0, model, engine
+        return model, engine
+
+    def start(slot: _Slot) -> None:
+        """Next pending slice plus up to batch - 1 further pending slices of the same shape and group count."""
+        first = pending.popleft()
+        group = [first]
+        key = shape_key(first)
+        for i in list(pending):
+            if len(group) >= max(1, int(batch)):
+                break
+            if shape_key(i) == key:
+                pending.remove(i)
+                group.append(i)
+        built = [start_one(i) for i in group]
+        slot.indices, slot.done = group, 0
+        slot.models = [b[0] for b in built]
+        slot.engines = [b[1] for b in built]
 
     def finish(slot: _Slot) -> None:
-        i, eng = slot.index, slot.engine
-        img = torch.view_as_complex(eng.image.clone())
-        img.record_stream(caller)
-        images[i] = img
-        if return_kspace:
-            k = torch.view_as_complex(eng.k_out.clone())
-            k.record_stream(caller)
-            ksp_out[i] = k
-        if return_traces or debug:
-            acc = eng.loss[:iters].clone()
-            acc.record_stream(caller)
-            losses[i] = acc
-        slot.index, slot.model, slot.engine = -1, None, None
+        for i, eng in zip(slot.indices, slot.engines):
+            img = torch.view_as_complex(eng.image.clone())
+            img.record_stream(caller)
+            images[i] = img
+            if return_kspace:
+                k = torch.view_as_complex(eng.k_out.clone())
+                k.record_stream(caller)
+                ksp_out[i] = k
+            if return_traces or debug:
+                acc = eng.loss[:iters].clone()
+                acc.record_stream(caller)
+                losses[i] = acc
+        slot.indices, slot.models, slot.engines = [], [], []
 
     active = True
     while active:
         active = False
         for slot in slots:
             with torch.cuda.stream(slot.stream):
-                if slot.index < 0:
+                if not slot.indices:
                     if not pending:
                         continue
-                    start(slot, pending.popleft())
+                    start(slot)
                 end = min(iters, slot.done + chunk)
-                slot.engine.run(lambdas, learning_rate, slot.done, end)
+                run_batched(slot.engines, lambdas, learning_rate, slot.done, end)
                 slot.done = end
                 if slot.done >= iters:
                     finish(slot)

@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "fit_batch.cuh"
 
 // launch helpers implemented in forward_model.cu
 int immoco_rows_static(const float* in, float* out, int h, int w, const float* tw_w,
@@ -15,20 +16,18 @@ int immoco_motion_rows_fwd(const float* image, const float* disp, const float* i
 int immoco_motion_rows_bwd(const float* d_c, const float* image, const float* disp, const float* ident,
                            const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp,
                            int h, int w, void* stream);
-int immoco_rows_fwd_fused(const float* image, const float* disp, const float* ident, const immoco_lines* lines,
-                          const float* tw_w, float* c_out, int h, int w, void* stream);
-int immoco_rows_bwd_fused(const float* d_c, const float* image, const float* disp, const float* ident,
-                          const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp, int h, int w,
-                          int64_t* fx, const uint32_t* dmax_bits, void* stream);
-int immoco_colpass_loss_zero(float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
-                             const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream);
+int immoco_rows_fwd_fused_batch(const FitBatch& b, const float* ident, const float* tw_w, int h, int w, void* stream);
+int immoco_rows_bwd_fused_batch(const FitBatch& b, const float* ident, const float* tw_w, int h, int w, bool det,
+                                void* stream);
+int immoco_colpass_loss_batch(const FitBatch& b, const float* tw_h, int h, int w, int zero_input, void* stream);
 int immoco_colpass_loss_slots(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
                               const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream);
-int immoco_grad_entropy_slots(const float* image, float grad_scale, double* loss_acc, float* d_image,
-                              int accumulate, int h, int w, double* loss_slots, void* stream);
-int immoco_d_image_finalize(float* d_image, int64_t* fx, const uint32_t* dmax_bits, int h, int w, void* stream);
+int immoco_grad_entropy_batch(const FitBatch& b, float grad_scale, int accumulate, int h, int w, void* stream);
+int immoco_d_image_finalize_batch(const FitBatch& b, int h, int w, void* stream);
 // mlp_tc.cu
 int immoco_mlp_bwd_tc_grid(int64_t n_points);
+int immoco_mlp_fwd_tc_batch(const MlpFwdBatch& b, int64_t n_points, int32_t width, int32_t act, int32_t out_tanh,
+                            void* stream);
 
 namespace {
 
@@ -435,61 +434,94 @@ extern "C" int immoco_set_profile_overlap(int32_t on) { g_profile_overlap = on ?
   } while (0)
 static inline int nop() { return 0; }
 
-extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_end,
-                              const float* lambdas_host, void* stream, immoco_profile* prof,
-                              int32_t profile_every) {
-  if (!f || !lambdas_host || it_begin < 0 || it_end < it_begin) return IMMOCO_ERR_BAD_ARG;
-  const int H = f->h, W = f->w, M = f->m;
-  if (H < 2 || W < 2 || M < 0 || M != f->lines.n_groups) return IMMOCO_ERR_BAD_ARG;
-  if (it_begin == it_end) return 0;
+// One batch of B fits of the same shape (h, w, m, network widths, grid descriptors), each with its own buffers,
+// masks and parameters, advanced in lock step: the latency-bound kernels (row / column passes, gradient
+// entropy, fixed-point finalize, MLP forward) are ONE launch over all instances (blockIdx.z / .y = instance),
+// the kernels that fill the GPU by themselves (hash grid, MLP backward, Adam) are issued per instance.
+static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, int32_t it_end,
+                        const float* lambdas_host, void* stream, immoco_profile* prof, int32_t profile_every) {
+  if (!fs || B < 1 || B > kMaxFitBatch || !lambdas_host || it_begin < 0 || it_end < it_begin) return IMMOCO_ERR_BAD_ARG;
+  const immoco_fit* f0 = fs[0];
+  if (!f0) return IMMOCO_ERR_BAD_ARG;
+  const int H = f0->h, W = f0->w, M = f0->m;
+  if (H < 2 || W < 2 || M < 0) return IMMOCO_ERR_BAD_ARG;
+  const int wi = f0->width_image, wm = f0->width_motion;
+  const bool det = f0->deterministic != 0;
+  const bool fuse_adam = det && f0->fuse_adam != 0;
   const int64_t P = (int64_t)H * W, MP = P * M;
-  const int wi = f->width_image, wm = f->width_motion;
+  for (int b = 0; b < B; ++b) {
+    const immoco_fit* f = fs[b];
+    if (!f || f->h != H || f->w != W || f->m != M || M != f->lines.n_groups) return IMMOCO_ERR_BAD_ARG;
+    if (f->width_image != wi || f->width_motion != wm || f->act_image != f0->act_image || f->act_motion != f0->act_motion)
+      return IMMOCO_ERR_BAD_ARG;
+    if ((f->deterministic != 0) != det || (det && (f->fuse_adam != 0) != fuse_adam)) return IMMOCO_ERR_BAD_ARG;
+    if (f->n_motion != f0->n_motion || f->n_image != f0->n_image || (f->n_motion & 3) != 0) return IMMOCO_ERR_BAD_ARG;
+    if ((f->loss_slots == nullptr) != (f0->loss_slots == nullptr)) return IMMOCO_ERR_BAD_ARG;
+    if (det) {
+      if (!f->loss_slots || !f->d_image_fx || !f->dc_max_bits || !f->mlp_part_image || !f->csr_image.row_ptr ||
+          !f->csr_image.taps)
+        return IMMOCO_ERR_BAD_ARG;
+      if (M > 0 && (!f->mlp_part_motion || !f->csr_motion.row_ptr || !f->csr_motion.taps)) return IMMOCO_ERR_BAD_ARG;
+      if (f->csr_image.n_points != P || (M > 0 && f->csr_motion.n_points != MP)) return IMMOCO_ERR_BAD_ARG;
+    }
+  }
+  if (it_begin == it_end) return 0;
   // parameter views: [motion | image], each [W1 (width x 32) | W2 (16 x width) | table]
-  float* pm = f->params;
-  float* pi = f->params + f->n_motion;
-  float* gm = f->grads;
-  float* gi = f->grads + f->n_motion;
   const int64_t mlp_m = (int64_t)wm * 32 + 16 * (int64_t)wm;
   const int64_t mlp_i = (int64_t)wi * 32 + 16 * (int64_t)wi;
-  if ((f->n_motion & 3) != 0) return IMMOCO_ERR_BAD_ARG;   // keeps the image half 16-byte aligned
-
-  // ---- reproducible accumulation ---------------------------------------------------------------------
-  const bool det = f->deterministic != 0;
-  const bool fuse_adam = det && f->fuse_adam != 0;
-  if (det) {
-    if (!f->loss_slots || !f->d_image_fx || !f->dc_max_bits || !f->mlp_part_image || !f->csr_image.row_ptr ||
-        !f->csr_image.taps)
-      return IMMOCO_ERR_BAD_ARG;
-    if (M > 0 && (!f->mlp_part_motion || !f->csr_motion.row_ptr || !f->csr_motion.taps)) return IMMOCO_ERR_BAD_ARG;
-    if (f->csr_image.n_points != P || (M > 0 && f->csr_motion.n_points != MP)) return IMMOCO_ERR_BAD_ARG;
-  }
+  const int64_t n_mot = f0->n_motion;
   int slots[2] = {0, 0};
-  if (f->loss_slots) IMMOCO_TRY(immoco_fit_loss_slots(H, W, slots));
+  if (f0->loss_slots) IMMOCO_TRY(immoco_fit_loss_slots(H, W, slots));
   const int per_iter = slots[0] + slots[1];
   const int n_part_i = det ? immoco_mlp_bwd_tc_grid(P) : 0;
   const int n_part_m = (det && M > 0) ? immoco_mlp_bwd_tc_grid(MP) : 0;
-  float* mom1_m = f->exp_avg;
-  float* mom2_m = f->exp_avg_sq;
-  float* mom1_i = f->exp_avg + f->n_motion;
-  float* mom2_i = f->exp_avg_sq + f->n_motion;
 
   cudaStream_t ms = (cudaStream_t)stream;
   AuxStream* aux = (g_overlap && M > 0) ? aux_for(ms) : nullptr;
   bool forked = false;          // aux currently carries work that `ms` has not joined
   bool zero_pending = false;    // the previous iteration left its gradients for the deferred memset
 
-  const bool fuse_rows = g_fuse_rows != 0 || det;
-  // the fused row launch ADDS into c_tmp; the column pass re-zeroes it for the next iteration
-  if (fuse_rows && cudaMemsetAsync(f->c_tmp, 0, (size_t)P * 2 * sizeof(float), ms) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
-  // the per-iteration maxima are integer atomicMax targets: clear the ones this call owns
-  if (det && cudaMemsetAsync(f->dc_max_bits + it_begin, 0, (size_t)(it_end - it_begin) * sizeof(uint32_t), ms) != cudaSuccess)
-    return IMMOCO_ERR_BAD_ARG;
+  const bool fuse_rows = g_fuse_rows != 0 || det || B > 1;
+  for (int b = 0; b < B; ++b) {
+    const immoco_fit* f = fs[b];
+    // the fused row launch ADDS into c_tmp; the column pass re-zeroes it for the next iteration
+    if (fuse_rows && cudaMemsetAsync(f->c_tmp, 0, (size_t)P * 2 * sizeof(float), ms) != cudaSuccess) return IMMOCO_ERR_BAD_ARG;
+    // the per-iteration maxima are integer atomicMax targets: clear the ones this call owns
+    if (det && cudaMemsetAsync(f->dc_max_bits + it_begin, 0, (size_t)(it_end - it_begin) * sizeof(uint32_t), ms) != cudaSuccess)
+      return IMMOCO_ERR_BAD_ARG;
+  }
+  auto zero_grads = [&](cudaStream_t st) {
+    for (int b = 0; b < B; ++b) cudaMemsetAsync(fs[b]->grads, 0, (size_t)(n_mot + f0->n_image) * sizeof(float), st);
+  };
 
   for (int it = it_begin; it < it_end; ++it) {
-    double* loss = f->loss + 2 * (int64_t)it;
-    double* slots_dc = f->loss_slots ? f->loss_slots + (size_t)it * per_iter : nullptr;
-    double* slots_ge = slots_dc ? slots_dc + slots[0] : nullptr;
-    uint32_t* dmax = det ? f->dc_max_bits + it : nullptr;
+    // ---- this iteration's view of the batch -----------------------------------------------------------
+    FitBatch fb = {};
+    MlpFwdBatch mi = {}, mm = {};
+    fb.n = mi.n = mm.n = B;
+    for (int b = 0; b < B; ++b) {
+      const immoco_fit* f = fs[b];
+      FitBatchInst& a = fb.inst[b];
+      a.image = (const float2*)f->image;
+      a.disp = (const float2*)f->disp;
+      a.c_tmp = (float2*)f->c_tmp;
+      a.k_in = (const float2*)f->k_in;
+      a.k_out = (float2*)f->k_out;
+      a.d_c = (float2*)f->d_c;
+      a.d_image = (float2*)f->d_image;
+      a.d_disp = (float2*)f->d_disp;
+      a.fx = det ? (long long*)f->d_image_fx : nullptr;
+      a.dmax = det ? f->dc_max_bits + it : nullptr;
+      a.loss_dc = f->loss + 2 * (int64_t)it;
+      a.loss_ge = a.loss_dc + 1;
+      a.slots_dc = f->loss_slots ? f->loss_slots + (size_t)it * per_iter : nullptr;
+      a.slots_ge = a.slots_dc ? a.slots_dc + slots[0] : nullptr;
+      a.lines = f->lines;
+      float* pm = f->params;
+      float* pi = f->params + n_mot;
+      mi.enc[b] = (const float2*)f->enc_image; mi.w1[b] = pi; mi.w2[b] = pi + (int64_t)wi * 32; mi.out[b] = (float2*)f->image;
+      mm.enc[b] = (const float2*)f->enc_motion; mm.w1[b] = pm; mm.w2[b] = pm + (int64_t)wm * 32; mm.out[b] = (float2*)f->disp;
+    }
     cudaEvent_t* ev = nullptr;
     if (prof && profile_every > 0 && (it % profile_every) == profile_every - 1 && prof->used < prof->capacity)
       ev = prof->ev + (size_t)(prof->used++) * prof_stride(prof);
@@ -512,45 +544,64 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     const bool defer_zero = two && g_deferred_zero != 0 && !det;
     if (zero_pending && !defer_zero) {      // the previous iteration deferred its zeroing, this one cannot
       if (aux) cudaStreamWaitEvent(ms, aux->adam_i_done, 0);
-      cudaMemsetAsync(f->grads, 0, (size_t)(f->n_motion + f->n_image) * sizeof(float), ms);
+      zero_grads(ms);
       zero_pending = false;
     }
     if (ev) cudaEventRecord(ev[0], ms);
+// per-instance launches of one profile slot
+#define EACH(expr)                                    \
+  [&]() -> int {                                      \
+    for (int b = 0; b < B; ++b) {                     \
+      const immoco_fit* f = fs[b];                    \
+      [[maybe_unused]] float* pm = f->params;                  \
+      [[maybe_unused]] float* pi = f->params + n_mot;          \
+      [[maybe_unused]] float* gm = f->grads;                   \
+      [[maybe_unused]] float* gi = f->grads + n_mot;           \
+      [[maybe_unused]] float* mom1_m = f->exp_avg;             \
+      [[maybe_unused]] float* mom2_m = f->exp_avg_sq;          \
+      [[maybe_unused]] float* mom1_i = f->exp_avg + n_mot;     \
+      [[maybe_unused]] float* mom2_i = f->exp_avg_sq + n_mot;  \
+      int e__ = (expr);                               \
+      if (e__ != 0) return e__;                       \
+    }                                                 \
+    return 0;                                         \
+  }()
     // ---- forward -------------------------------------------------------------------------------
-    K(0, is, immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is));
-    K(1, is, immoco_mlp_fwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->image, P, wi, f->act_image, 0, is));
+    K(0, is, EACH(immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is)));
+    K(1, is, immoco_mlp_fwd_tc_batch(mi, P, wi, f0->act_image, 0, is));
     // gradient entropy needs the image only; it initialises d_image (lambda folded in)
-    K(7, is, immoco_grad_entropy_slots(f->image, lambdas_host[it], loss + 1, f->d_image, 0, H, W, slots_ge, is));
+    K(7, is, immoco_grad_entropy_batch(fb, lambdas_host[it], 0, H, W, is));
     if (two) cudaEventRecord(aux->join_fwd, aux->stream);
-    K(2, ms, M > 0 ? immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream) : nop());
+    K(2, ms, M > 0 ? EACH(immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream)) : nop());
     if (defer_zero && zero_pending) {
       // gradients of the previous iteration were consumed by both Adam launches (Adam_m precedes this point
       // on `ms`, Adam_i is awaited through its event): zero them now, beside the SM-bound kernels that follow
       cudaEventRecord(aux->zero_start, ms);
       cudaStreamWaitEvent(aux->zero_stream, aux->zero_start, 0);
       cudaStreamWaitEvent(aux->zero_stream, aux->adam_i_done, 0);
-      cudaMemsetAsync(f->grads, 0, (size_t)(f->n_motion + f->n_image) * sizeof(float), aux->zero_stream);
+      zero_grads(aux->zero_stream);
       cudaEventRecord(aux->zero_done, aux->zero_stream);
     }
-    K(3, ms, M > 0 ? immoco_mlp_fwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->disp, MP, wm, f->act_motion, 1, stream) : nop());
+    K(3, ms, M > 0 ? immoco_mlp_fwd_tc_batch(mm, MP, wm, f0->act_motion, 1, stream) : nop());
     if (two) cudaStreamWaitEvent(ms, aux->join_fwd, 0);
     if (fuse_rows) {      // slot 4 (static row pass) is folded into slot 5, slot 8 into slot 9
       K(4, ms, nop());
-      K(5, ms, immoco_rows_fwd_fused(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
-      K(6, ms, immoco_colpass_loss_zero(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, slots_dc, dmax, stream));
-      K(9, ms, immoco_rows_bwd_fused(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->d_image,
-                                     f->d_disp, H, W, det ? f->d_image_fx : nullptr, dmax, stream));
+      K(5, ms, immoco_rows_fwd_fused_batch(fb, f0->coords_image, f0->tw_w, H, W, stream));
+      K(6, ms, immoco_colpass_loss_batch(fb, f0->tw_h, H, W, 1, stream));
+      K(9, ms, immoco_rows_bwd_fused_batch(fb, f0->coords_image, f0->tw_w, H, W, det, stream));
       if (det) {
         // d_image += the fixed-point plane; on the image branch (it is the only consumer), beside MLPm_b
         if (two) { cudaEventRecord(aux->rows_done, ms); cudaStreamWaitEvent(aux->stream, aux->rows_done, 0); }
-        K(8, is, immoco_d_image_finalize(f->d_image, f->d_image_fx, dmax, H, W, is));
+        K(8, is, immoco_d_image_finalize_batch(fb, H, W, is));
       } else {
         K(8, ms, nop());
       }
-    } else {
+    } else {      // four separate launches (A/B check; single instance, float-atomic mode only)
+      const immoco_fit* f = f0;
+      const FitBatchInst& a = fb.inst[0];
       K(4, ms, immoco_rows_static(f->image, f->c_tmp, H, W, f->tw_w, nullptr, f->lines.static_w, 0, false, stream));
       K(5, ms, immoco_motion_rows_fwd(f->image, f->disp, f->coords_image, &f->lines, f->tw_w, f->c_tmp, H, W, stream));
-      K(6, ms, immoco_colpass_loss_slots(f->c_tmp, f->k_in, f->k_out, f->d_c, loss, f->tw_h, H, W, slots_dc, nullptr, stream));
+      K(6, ms, immoco_colpass_loss_slots(f->c_tmp, f->k_in, f->k_out, f->d_c, a.loss_dc, f->tw_h, H, W, a.slots_dc, nullptr, stream));
       // ---- backward ----------------------------------------------------------------------------
       K(8, ms, immoco_rows_static(f->d_c, f->d_image, H, W, f->tw_w, f->lines.static_w, nullptr, 1, true, stream));
       K(9, ms, M > 0 ? immoco_motion_rows_bwd(f->d_c, f->image, f->disp, f->coords_image, &f->lines, f->tw_w,
@@ -562,68 +613,85 @@ extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_
     }
     if (det) {
       // ---- backward + update, reproducible: per-CTA weight-gradient blocks, row-sorted gathers -----------
-      K(10, ms, M > 0 ? immoco_mlp_bwd_partials(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion,
-                                                f->mlp_part_motion, MP, wm, f->act_motion, stream) : nop());
+      K(10, ms, M > 0 ? EACH(immoco_mlp_bwd_partials(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion,
+                                                     f->mlp_part_motion, MP, wm, f->act_motion, stream)) : nop());
       if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
       if (fuse_adam) {
-        K(11, ms, M > 0 ? immoco_hashgrid_bwd_csr_adam(&f->grid_motion, &f->csr_motion, f->d_enc_motion, pm + mlp_m,
-                                                       mom1_m + mlp_m, mom2_m + mlp_m, nullptr, f->lr, f->beta1,
-                                                       f->beta2, f->eps, it + 1, stream) : nop());
+        K(11, ms, M > 0 ? EACH(immoco_hashgrid_bwd_csr_adam(&f->grid_motion, &f->csr_motion, f->d_enc_motion, pm + mlp_m,
+                                                            mom1_m + mlp_m, mom2_m + mlp_m, nullptr, f->lr, f->beta1,
+                                                            f->beta2, f->eps, it + 1, stream)) : nop());
       } else {
-        K(11, ms, M > 0 ? immoco_hashgrid_bwd_csr(&f->grid_motion, &f->csr_motion, f->d_enc_motion, gm + mlp_m, stream) : nop());
+        K(11, ms, M > 0 ? EACH(immoco_hashgrid_bwd_csr(&f->grid_motion, &f->csr_motion, f->d_enc_motion, gm + mlp_m, stream)) : nop());
       }
-      K(12, is, immoco_mlp_bwd_partials(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image,
-                                        f->mlp_part_image, P, wi, f->act_image, is));
+      K(12, is, EACH(immoco_mlp_bwd_partials(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image,
+                                             f->mlp_part_image, P, wi, f->act_image, is)));
       if (fuse_adam) {
-        K(13, is, immoco_hashgrid_bwd_csr_adam(&f->grid_image, &f->csr_image, f->d_enc_image, pi + mlp_i, mom1_i + mlp_i,
-                                               mom2_i + mlp_i, nullptr, f->lr, f->beta1, f->beta2, f->eps, it + 1, is));
+        K(13, is, EACH(immoco_hashgrid_bwd_csr_adam(&f->grid_image, &f->csr_image, f->d_enc_image, pi + mlp_i, mom1_i + mlp_i,
+                                                    mom2_i + mlp_i, nullptr, f->lr, f->beta1, f->beta2, f->eps, it + 1, is)));
       } else {
-        K(13, is, immoco_hashgrid_bwd_csr(&f->grid_image, &f->csr_image, f->d_enc_image, gi + mlp_i, is));
+        K(13, is, EACH(immoco_hashgrid_bwd_csr(&f->grid_image, &f->csr_image, f->d_enc_image, gi + mlp_i, is)));
       }
       if (ev) cudaEventRecord(ev[1 + 2 * 14], ms);
       if (M > 0) {
-        IMMOCO_TRY(immoco_adam_step_partials(pm, f->mlp_part_motion, n_part_m, mom1_m, mom2_m, mlp_m, f->lr, f->beta1,
-                                             f->beta2, f->eps, it + 1, stream));
+        IMMOCO_TRY(EACH(immoco_adam_step_partials(pm, f->mlp_part_motion, n_part_m, mom1_m, mom2_m, mlp_m, f->lr, f->beta1,
+                                                  f->beta2, f->eps, it + 1, stream)));
         if (!fuse_adam)
-          IMMOCO_TRY(immoco_adam_step(pm + mlp_m, gm + mlp_m, mom1_m + mlp_m, mom2_m + mlp_m, f->n_motion - mlp_m, f->lr,
-                                      f->beta1, f->beta2, f->eps, it + 1, 0, stream));
+          IMMOCO_TRY(EACH(immoco_adam_step(pm + mlp_m, gm + mlp_m, mom1_m + mlp_m, mom2_m + mlp_m, n_mot - mlp_m, f->lr,
+                                           f->beta1, f->beta2, f->eps, it + 1, 0, stream)));
       }
       if (ev) { cudaEventRecord(ev[2 + 2 * 14], ms); cudaEventRecord(ev[1 + 2 * 15], (cudaStream_t)is); }
-      IMMOCO_TRY(immoco_adam_step_partials(pi, f->mlp_part_image, n_part_i, mom1_i, mom2_i, mlp_i, f->lr, f->beta1,
-                                           f->beta2, f->eps, it + 1, is));
+      IMMOCO_TRY(EACH(immoco_adam_step_partials(pi, f->mlp_part_image, n_part_i, mom1_i, mom2_i, mlp_i, f->lr, f->beta1,
+                                                f->beta2, f->eps, it + 1, is)));
       if (!fuse_adam)
-        IMMOCO_TRY(immoco_adam_step(pi + mlp_i, gi + mlp_i, mom1_i + mlp_i, mom2_i + mlp_i, f->n_image - mlp_i, f->lr,
-                                    f->beta1, f->beta2, f->eps, it + 1, 0, is));
+        IMMOCO_TRY(EACH(immoco_adam_step(pi + mlp_i, gi + mlp_i, mom1_i + mlp_i, mom2_i + mlp_i, f->n_image - mlp_i, f->lr,
+                                         f->beta1, f->beta2, f->eps, it + 1, 0, is)));
       if (ev) cudaEventRecord(ev[2 + 2 * 15], (cudaStream_t)is);
       continue;
     }
-    K(10, ms, M > 0 ? immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
-                                     gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream) : nop());
+    K(10, ms, M > 0 ? EACH(immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
+                                          gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream)) : nop());
     if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
-    K(11, ms, M > 0 ? immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream) : nop());
-    K(12, is, immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
-                             gi + (int64_t)wi * 32, P, wi, f->act_image, is));
-    K(13, is, immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is));
+    K(11, ms, M > 0 ? EACH(immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream)) : nop());
+    K(12, is, EACH(immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
+                                  gi + (int64_t)wi * 32, P, wi, f->act_image, is)));
+    K(13, is, EACH(immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is)));
     // ---- update (zero_grad fused), one launch per INR so each follows its own branch ---------------
     // (the LAST iteration of the call zeroes inside Adam, so the gradients are clean when the call returns)
     const int adam_zeroes = (defer_zero && it + 1 < it_end) ? 0 : 1;
-    K(14, ms, M > 0 ? immoco_adam_step(pm, gm, f->exp_avg, f->exp_avg_sq, f->n_motion, f->lr, f->beta1, f->beta2,
-                                       f->eps, it + 1, adam_zeroes, stream) : nop());
-    K(15, is, immoco_adam_step(pi, gi, f->exp_avg + f->n_motion, f->exp_avg_sq + f->n_motion, f->n_image, f->lr,
-                               f->beta1, f->beta2, f->eps, it + 1, adam_zeroes, is));
+    K(14, ms, M > 0 ? EACH(immoco_adam_step(pm, gm, f->exp_avg, f->exp_avg_sq, n_mot, f->lr, f->beta1, f->beta2,
+                                            f->eps, it + 1, adam_zeroes, stream)) : nop());
+    K(15, is, EACH(immoco_adam_step(pi, gi, f->exp_avg + n_mot, f->exp_avg_sq + n_mot, f->n_image, f->lr,
+                                    f->beta1, f->beta2, f->eps, it + 1, adam_zeroes, is)));
     if (!adam_zeroes) {
       cudaEventRecord(aux->adam_i_done, aux->stream);
       zero_pending = true;
     }
   }
+#undef EACH
   if (forked) {
     cudaEventRecord(aux->join_end, aux->stream);
     cudaStreamWaitEvent(ms, aux->join_end, 0);
   }
-  if (f->loss_slots) {      // per-CTA loss slots of this call's iterations -> f->loss, added in slot order
+  if (f0->loss_slots) {      // per-CTA loss slots of this call's iterations -> loss, added in slot order
     const int n = 2 * (it_end - it_begin);
-    loss_reduce_kernel<<<(n + 127) / 128, 128, 0, ms>>>(f->loss_slots, per_iter, slots[0], f->loss, it_begin, it_end);
-    IMMOCO_LAUNCH_CHECK();
+    for (int b = 0; b < B; ++b) {
+      loss_reduce_kernel<<<(n + 127) / 128, 128, 0, ms>>>(fs[b]->loss_slots, per_iter, slots[0], fs[b]->loss, it_begin, it_end);
+      IMMOCO_LAUNCH_CHECK();
+    }
   }
   return 0;
 }
+
+extern "C" int immoco_fit_run(const immoco_fit* f, int32_t it_begin, int32_t it_end,
+                              const float* lambdas_host, void* stream, immoco_profile* prof,
+                              int32_t profile_every) {
+  return fit_run_impl(&f, 1, it_begin, it_end, lambdas_host, stream, prof, profile_every);
+}
+
+extern "C" int immoco_fit_run_batched(const immoco_fit* const* fits, int32_t n_fits, int32_t it_begin, int32_t it_end,
+                                      const float* lambdas_host, void* stream, immoco_profile* prof,
+                                      int32_t profile_every) {
+  return fit_run_impl(fits, n_fits, it_begin, it_end, lambdas_host, stream, prof, profile_every);
+}
+
+extern "C" int immoco_max_fit_batch(void) { return kMaxFitBatch; }

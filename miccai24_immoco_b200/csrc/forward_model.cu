@@ -9,6 +9,7 @@
 // leave shared memory.  All transforms are centred and un-normalised.
 #include "common.cuh"
 #include "fft.cuh"
+#include "fit_batch.cuh"
 
 namespace {
 
@@ -167,12 +168,18 @@ fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, int H, 
 // CPC adjacent columns per CTA: 4 (64-byte segments) when that still gives every SM a CTA, else 2
 template <int CPC>
 __global__ void __launch_bounds__(kThreads)
-colpass_loss_kernel(const float2* __restrict__ c_in, const float2* __restrict__ k_in,
-                    float2* __restrict__ k_out, float2* __restrict__ d_c, double* __restrict__ loss_acc,
-                    int H, int W, const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
-                    float2* __restrict__ zero_after_load, double* __restrict__ loss_slots,
-                    uint32_t* __restrict__ dmax_bits) {
+colpass_loss_kernel(const __grid_constant__ FitBatch batch, int H, int W, const __grid_constant__ FftPlan plan,
+                    const float2* __restrict__ tw_g, int zero_input) {
   pdl_wait();
+  const FitBatchInst& inst = batch.inst[blockIdx.z];        // blockIdx.z = instance (fit_batch.cuh)
+  const float2* __restrict__ c_in = inst.c_tmp;
+  const float2* __restrict__ k_in = inst.k_in;
+  float2* __restrict__ k_out = inst.k_out;
+  float2* __restrict__ d_c = inst.d_c;
+  double* __restrict__ loss_acc = inst.loss_dc;
+  double* __restrict__ loss_slots = inst.slots_dc;
+  uint32_t* __restrict__ dmax_bits = inst.dmax;
+  float2* __restrict__ zero_after_load = zero_input ? inst.c_tmp : nullptr;
   extern __shared__ __align__(16) float2 sm2[];
   __shared__ float red[kThreads / 32];
   __shared__ float redmax[kThreads / 32];
@@ -349,15 +356,19 @@ motion_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restric
 // c_out, zero-weight lines skipped); blockIdx.y == 1 + m -> pruned rows of movement group m.  c_out must be
 // zero on entry (colpass_loss_kernel re-zeroes it after loading).  One launch instead of two dependent ones.
 __global__ void __launch_bounds__(kThreads)
-rows_fwd_fused_kernel(const float2* __restrict__ image, const float2* __restrict__ disp,
-                      const float2* __restrict__ ident, const __grid_constant__ immoco_lines lines,
-                      const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g,
-                      float2* __restrict__ c_out, int H, int W) {
+rows_fwd_fused_kernel(const __grid_constant__ FitBatch batch, const float2* __restrict__ ident,
+                      const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g, int H, int W) {
   pdl_wait();
+  const FitBatchInst& inst = batch.inst[blockIdx.z];
+  const float2* __restrict__ image = inst.image;
+  const float2* __restrict__ disp = inst.disp;
+  float2* __restrict__ c_out = inst.c_tmp;
+  const immoco_lines& lines = inst.lines;
   if (blockIdx.y == 0) {
     if ((int)blockIdx.x * kRowsPerCta >= H) return;
     rows_body<false, 1>(image, c_out, H, W, plan, tw_g, nullptr, lines.static_w, 1.0f, 0, blockIdx.x);
   } else {
+    if ((int)blockIdx.y - 1 >= lines.n_groups) return;
     motion_rows_fwd_body(image, disp, ident, lines, tw_g, c_out, H, W, blockIdx.x, (int)blockIdx.y - 1);
   }
 }
@@ -463,18 +474,23 @@ motion_rows_bwd_kernel(const float2* __restrict__ d_c, const float2* __restrict_
 // d_image itself (it holds the gradient-entropy term) is only touched by d_image_finalize_kernel afterwards.
 template <bool DET>
 __global__ void __launch_bounds__(kThreads)
-rows_bwd_fused_kernel(const float2* __restrict__ d_c, const float2* __restrict__ image,
-                      const float2* __restrict__ disp, const float2* __restrict__ ident,
-                      const __grid_constant__ immoco_lines lines, const __grid_constant__ FftPlan plan,
-                      const float2* __restrict__ tw_g, float2* __restrict__ d_image,
-                      float2* __restrict__ d_disp, int H, int W, long long* __restrict__ fx,
-                      const uint32_t* __restrict__ dmax_bits) {
+rows_bwd_fused_kernel(const __grid_constant__ FitBatch batch, const float2* __restrict__ ident,
+                      const __grid_constant__ FftPlan plan, const float2* __restrict__ tw_g, int H, int W) {
   pdl_wait();
-  const double sc = DET ? pow2_double(fx_exponent(*dmax_bits, W)) : 0.0;
+  const FitBatchInst& inst = batch.inst[blockIdx.z];
+  const float2* __restrict__ d_c = inst.d_c;
+  const float2* __restrict__ image = inst.image;
+  const float2* __restrict__ disp = inst.disp;
+  float2* __restrict__ d_image = inst.d_image;
+  float2* __restrict__ d_disp = inst.d_disp;
+  long long* __restrict__ fx = inst.fx;
+  const immoco_lines& lines = inst.lines;
+  const double sc = DET ? pow2_double(fx_exponent(*inst.dmax, W)) : 0.0;
   if (blockIdx.y == 0) {
     if ((int)blockIdx.x * kRowsPerCta >= H) return;
     rows_body<true, DET ? 2 : 1>(d_c, d_image, H, W, plan, tw_g, lines.static_w, nullptr, 1.0f, 1, blockIdx.x, fx, sc);
   } else {
+    if ((int)blockIdx.y - 1 >= lines.n_groups) return;
     motion_rows_bwd_body<DET>(d_c, image, disp, ident, lines, tw_g, d_image, d_disp, 1, H, W, blockIdx.x,
                               (int)blockIdx.y - 1, fx, sc);
   }
@@ -483,10 +499,12 @@ rows_bwd_fused_kernel(const float2* __restrict__ d_c, const float2* __restrict__
 // d_image += fixed-point plane (converted back with the iteration's scale); the plane is re-zeroed for the
 // next iteration.  One rounding per element whatever order the contributions arrived in.
 __global__ void __launch_bounds__(kThreads)
-d_image_finalize_kernel(float* __restrict__ d_image, long long* __restrict__ fx, const uint32_t* __restrict__ dmax_bits,
-                        int n, int W) {
+d_image_finalize_kernel(const __grid_constant__ FitBatch batch, int n, int W) {
   pdl_wait();
-  const double inv = pow2_double(-fx_exponent(*dmax_bits, W));
+  const FitBatchInst& inst = batch.inst[blockIdx.z];
+  float* __restrict__ d_image = reinterpret_cast<float*>(inst.d_image);
+  long long* __restrict__ fx = inst.fx;
+  const double inv = pow2_double(-fx_exponent(*inst.dmax, W));
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const long long q = fx[i];
     if (q != 0) {
@@ -508,9 +526,13 @@ __device__ __forceinline__ float ge_dloss_dg(float g) {
 }
 
 __global__ void __launch_bounds__(kThreads)
-grad_entropy_kernel(const float2* __restrict__ img, float grad_scale, double* __restrict__ loss_acc,
-                    float2* __restrict__ d_img, int accumulate, int H, int W, double* __restrict__ loss_slots) {
+grad_entropy_kernel(const __grid_constant__ FitBatch batch, float grad_scale, int accumulate, int H, int W) {
   pdl_wait();
+  const FitBatchInst& inst = batch.inst[blockIdx.z];
+  const float2* __restrict__ img = inst.image;
+  float2* __restrict__ d_img = inst.d_image;
+  double* __restrict__ loss_acc = inst.loss_ge;
+  double* __restrict__ loss_slots = inst.slots_ge;
   __shared__ float red[kThreads / 32];
   const int P = H * W;
   float part = 0.0f;
@@ -698,57 +720,72 @@ static int colpass_cpc(int w) { return ((w + kColsPerCta - 1) / kColsPerCta >= I
 static int colpass_grid(int w) { const int cpc = colpass_cpc(w); return (w + cpc - 1) / cpc; }
 static int grad_entropy_grid(int h, int w) { return (h * w + kThreads - 1) / kThreads; }
 
-static int colpass_launch(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
-                          const float* tw_h, int32_t h, int32_t w, float* zero_after_load, double* loss_slots,
-                          uint32_t* dmax_bits, void* stream) {
+static int colpass_launch(const FitBatch& b, const float* tw_h, int32_t h, int32_t w, int zero_input, void* stream) {
   const Plans p = make_plans(h, w);
   if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  if (b.n < 1 || b.n > kMaxFitBatch) return IMMOCO_ERR_BAD_ARG;
   const size_t smem = cols_smem(h);
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
-  const int grid = colpass_grid(w);
+  const dim3 grid(colpass_grid(w), 1, b.n);
   if (colpass_cpc(w) == kColsPerCta) {
     allow_smem(colpass_loss_kernel<kColsPerCta>, smem);
-    immoco_launch(colpass_loss_kernel<kColsPerCta>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream,
-        (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
-        (const float2*)tw_h, (float2*)zero_after_load, loss_slots, dmax_bits);
+    immoco_launch(colpass_loss_kernel<kColsPerCta>, grid, dim3(kThreads), smem, (cudaStream_t)stream, b, h, w, p.h,
+                  (const float2*)tw_h, zero_input);
   } else {
     allow_smem(colpass_loss_kernel<2>, smem);
-    immoco_launch(colpass_loss_kernel<2>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream,
-        (const float2*)c, (const float2*)k_in, (float2*)k_out, (float2*)d_c, loss_acc, h, w, p.h,
-        (const float2*)tw_h, (float2*)zero_after_load, loss_slots, dmax_bits);
+    immoco_launch(colpass_loss_kernel<2>, grid, dim3(kThreads), smem, (cudaStream_t)stream, b, h, w, p.h,
+                  (const float2*)tw_h, zero_input);
   }
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
 
+static FitBatch one_colpass(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
+                            double* loss_slots, uint32_t* dmax_bits) {
+  FitBatch b = {};
+  b.n = 1;
+  b.inst[0].c_tmp = (float2*)c;
+  b.inst[0].k_in = (const float2*)k_in;
+  b.inst[0].k_out = (float2*)k_out;
+  b.inst[0].d_c = (float2*)d_c;
+  b.inst[0].loss_dc = loss_acc;
+  b.inst[0].slots_dc = loss_slots;
+  b.inst[0].dmax = dmax_bits;
+  return b;
+}
+
 extern "C" int immoco_colpass_loss(const float* c, const float* k_in, float* k_out, float* d_c,
                                    double* loss_acc, const float* tw_h, int32_t h, int32_t w,
                                    void* stream) {
-  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, nullptr, nullptr, nullptr, stream);
+  return colpass_launch(one_colpass(c, k_in, k_out, d_c, loss_acc, nullptr, nullptr), tw_h, h, w, 0, stream);
 }
-// fit.cu: column pass that leaves its input buffer zeroed for the next iteration's fused row launch; the loss
-// goes to per-CTA slots when `loss_slots` is given, the largest cotangent component to *dmax_bits when given
-int immoco_colpass_loss_zero(float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
-                             const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream) {
-  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, c, loss_slots, dmax_bits, stream);
+// fit.cu: column pass of a batch of instances; zero_input: the pass leaves its input buffer zeroed for the next
+// iteration's fused row launch; the loss goes to per-CTA slots when an instance has slots_dc, the largest
+// cotangent component to *dmax when it has one
+int immoco_colpass_loss_batch(const FitBatch& b, const float* tw_h, int h, int w, int zero_input, void* stream) {
+  return colpass_launch(b, tw_h, h, w, zero_input, stream);
 }
 int immoco_colpass_loss_slots(const float* c, const float* k_in, float* k_out, float* d_c, double* loss_acc,
                               const float* tw_h, int h, int w, double* loss_slots, uint32_t* dmax_bits, void* stream) {
-  return colpass_launch(c, k_in, k_out, d_c, loss_acc, tw_h, h, w, nullptr, loss_slots, dmax_bits, stream);
+  return colpass_launch(one_colpass(c, k_in, k_out, d_c, loss_acc, loss_slots, dmax_bits), tw_h, h, w, 0, stream);
 }
 
-int immoco_grad_entropy_slots(const float* image, float grad_scale, double* loss_acc, float* d_image,
-                              int accumulate, int h, int w, double* loss_slots, void* stream) {
-  if (h < 1 || w < 1) return IMMOCO_ERR_BAD_ARG;
-  immoco_launch(grad_entropy_kernel, dim3(grad_entropy_grid(h, w)), dim3(kThreads), 0, (cudaStream_t)stream,
-                (const float2*)image, grad_scale, loss_acc, (float2*)d_image, accumulate, h, w, loss_slots);
+int immoco_grad_entropy_batch(const FitBatch& b, float grad_scale, int accumulate, int h, int w, void* stream) {
+  if (h < 1 || w < 1 || b.n < 1 || b.n > kMaxFitBatch) return IMMOCO_ERR_BAD_ARG;
+  immoco_launch(grad_entropy_kernel, dim3(grad_entropy_grid(h, w), 1, b.n), dim3(kThreads), 0, (cudaStream_t)stream, b,
+                grad_scale, accumulate, h, w);
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int immoco_grad_entropy(const float* image, float grad_scale, double* loss_acc,
                                    float* d_image, int32_t accumulate, int32_t h, int32_t w,
                                    void* stream) {
-  return immoco_grad_entropy_slots(image, grad_scale, loss_acc, d_image, accumulate, h, w, nullptr, stream);
+  FitBatch b = {};
+  b.n = 1;
+  b.inst[0].image = (const float2*)image;
+  b.inst[0].d_image = (float2*)d_image;
+  b.inst[0].loss_ge = loss_acc;
+  return immoco_grad_entropy_batch(b, grad_scale, accumulate, h, w, stream);
 }
 
 extern "C" int immoco_fit_loss_slots(int32_t h, int32_t w, int32_t out[2]) {
@@ -759,12 +796,12 @@ extern "C" int immoco_fit_loss_slots(int32_t h, int32_t w, int32_t out[2]) {
 }
 
 // d_image += the fixed-point cotangent plane of this iteration (deterministic mode), plane re-zeroed
-int immoco_d_image_finalize(float* d_image, int64_t* fx, const uint32_t* dmax_bits, int h, int w, void* stream) {
+int immoco_d_image_finalize_batch(const FitBatch& b, int h, int w, void* stream) {
+  if (b.n < 1 || b.n > kMaxFitBatch) return IMMOCO_ERR_BAD_ARG;
   const int n = 2 * h * w;
   int grid = (n + kThreads - 1) / kThreads;
   if (grid > IMMOCO_NUM_SMS * 8) grid = IMMOCO_NUM_SMS * 8;
-  immoco_launch(d_image_finalize_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, d_image, (long long*)fx,
-                dmax_bits, n, w);
+  immoco_launch(d_image_finalize_kernel, dim3(grid, 1, b.n), dim3(kThreads), 0, (cudaStream_t)stream, b, n, w);
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
@@ -787,42 +824,48 @@ int immoco_motion_rows_bwd(const float* d_c, const float* image, const float* di
   return launch_motion_bwd(d_c, image, disp, ident, lines, tw_w, d_image, d_disp, 1, h, w, (cudaStream_t)stream);
 }
 
-// Fused row launches of the fit loop (fit.cu).  c_out must be zero on entry of the forward one.
-int immoco_rows_fwd_fused(const float* image, const float* disp, const float* ident, const immoco_lines* lines,
-                          const float* tw_w, float* c_out, int h, int w, void* stream) {
+// Fused row launches of the fit loop (fit.cu) over a batch of instances of one shape.  Every instance's c_tmp
+// must be zero on entry of the forward one.
+static int max_lines_of(const FitBatch& b) {
+  int m = 1;
+  for (int i = 0; i < b.n; ++i)
+    if (b.inst[i].lines.max_lines > m) m = b.inst[i].lines.max_lines;
+  return m;
+}
+int immoco_rows_fwd_fused_batch(const FitBatch& b, const float* ident, const float* tw_w, int h, int w, void* stream) {
   const Plans p = make_plans(h, w);
   if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
+  if (b.n < 1 || b.n > kMaxFitBatch) return IMMOCO_ERR_BAD_ARG;
   const size_t smem = (size_t)(w + 2 * kRowsPerCta * w) * sizeof(float2);     // >= the motion rows' 2 W
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
   allow_smem(rows_fwd_fused_kernel, smem);
-  dim3 grid(h, 1 + lines->n_groups);
-  immoco_launch(rows_fwd_fused_kernel, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)image,
-                (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w, (float2*)c_out, h, w);
+  dim3 grid(h, 1 + b.inst[0].lines.n_groups, b.n);
+  immoco_launch(rows_fwd_fused_kernel, grid, dim3(kThreads), smem, (cudaStream_t)stream, b, (const float2*)ident, p.w,
+                (const float2*)tw_w, h, w);
   IMMOCO_LAUNCH_CHECK();
   return 0;
 }
-// fx != nullptr: deterministic mode (fixed-point accumulation, d_image itself untouched until the finalize)
-int immoco_rows_bwd_fused(const float* d_c, const float* image, const float* disp, const float* ident,
-                          const immoco_lines* lines, const float* tw_w, float* d_image, float* d_disp, int h, int w,
-                          int64_t* fx, const uint32_t* dmax_bits, void* stream) {
+// det: deterministic mode (fixed-point accumulation into inst.fx, d_image itself untouched until the finalize)
+int immoco_rows_bwd_fused_batch(const FitBatch& b, const float* ident, const float* tw_w, int h, int w, bool det,
+                                void* stream) {
   const Plans p = make_plans(h, w);
   if (!p.ok) return IMMOCO_ERR_UNSUPPORTED;
-  if (fx && !dmax_bits) return IMMOCO_ERR_BAD_ARG;
+  if (b.n < 1 || b.n > kMaxFitBatch) return IMMOCO_ERR_BAD_ARG;
+  for (int i = 0; i < b.n; ++i)
+    if (det && (!b.inst[i].fx || !b.inst[i].dmax)) return IMMOCO_ERR_BAD_ARG;
   size_t smem = (size_t)(w + 2 * kRowsPerCta * w) * sizeof(float2);
-  const size_t smem_m = (size_t)w * sizeof(float2) + (size_t)lines->max_lines * (sizeof(float2) + sizeof(int));
+  const size_t smem_m = (size_t)w * sizeof(float2) + (size_t)max_lines_of(b) * (sizeof(float2) + sizeof(int));
   if (smem_m > smem) smem = smem_m;
   if (smem > 200 * 1024) return IMMOCO_ERR_UNSUPPORTED;
-  dim3 grid(h, 1 + lines->n_groups);
-  if (fx) {
+  dim3 grid(h, 1 + b.inst[0].lines.n_groups, b.n);
+  if (det) {
     allow_smem(rows_bwd_fused_kernel<true>, smem);
-    immoco_launch(rows_bwd_fused_kernel<true>, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)d_c,
-                  (const float2*)image, (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w,
-                  (float2*)d_image, (float2*)d_disp, h, w, (long long*)fx, dmax_bits);
+    immoco_launch(rows_bwd_fused_kernel<true>, grid, dim3(kThreads), smem, (cudaStream_t)stream, b, (const float2*)ident,
+                  p.w, (const float2*)tw_w, h, w);
   } else {
     allow_smem(rows_bwd_fused_kernel<false>, smem);
-    immoco_launch(rows_bwd_fused_kernel<false>, grid, dim3(kThreads), smem, (cudaStream_t)stream, (const float2*)d_c,
-                  (const float2*)image, (const float2*)disp, (const float2*)ident, *lines, p.w, (const float2*)tw_w,
-                  (float2*)d_image, (float2*)d_disp, h, w, (long long*)nullptr, (const uint32_t*)nullptr);
+    immoco_launch(rows_bwd_fused_kernel<false>, grid, dim3(kThreads), smem, (cudaStream_t)stream, b, (const float2*)ident,
+                  p.w, (const float2*)tw_w, h, w);
   }
   IMMOCO_LAUNCH_CHECK();
   return 0;

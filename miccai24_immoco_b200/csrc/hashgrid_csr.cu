@@ -119,8 +119,9 @@ __device__ __forceinline__ void finish_row(uint32_t row, float gx, float gy, con
 }
 
 // taps per thread and trip of the narrow path: all index records first, then all gathers, then the
-// ordered sum -- 8 independent L2 round trips in flight per thread (a fine-level row has ~6 taps: one trip)
-constexpr int kUnroll = 8;
+// ordered sum -- 4 independent L2 round trips in flight per thread (8 measured slower: 282 vs 269 us for the
+// 3-D grid at C2; the gather sits at the measured L2 rate for unpaired 8-byte gathers, profiles/round2_l2_peaks.json)
+constexpr int kUnroll = 4;
 
 template <bool ADAM>
 __global__ void __launch_bounds__(kThreads)

@@ -470,6 +470,42 @@ class FitEngine:
             self.model.image_inr.params.copy_(self.params[self.n_motion:])
 
 
+def run_batched(engines, lambdas: List[float], learning_rate: float, it_begin: int = 0,
+                it_end: Optional[int] = None, profile=None, profile_every: int = 0) -> None:
+    """Iterations [it_begin, it_end) of SEVERAL fits of one shape in lock step (``immoco_fit_run_batched``): the
+    latency-bound kernels of an iteration are issued once for all instances, the GPU-filling ones per instance.
+    Every engine ends up exactly where its own ``run`` would have put it (bit for bit in deterministic mode)."""
+    engines = list(engines)
+    if not engines:
+        return
+    if len(engines) == 1:
+        engines[0].run(lambdas, learning_rate, it_begin, it_end, profile, profile_every)
+        return
+    lib = nat.lib()
+    if len(engines) > lib.immoco_max_fit_batch():
+        raise ValueError(f"at most {lib.immoco_max_fit_batch()} fits per batch")
+    it_end = len(lambdas) if it_end is None else it_end
+    e0 = engines[0]
+    for e in engines:
+        if it_end > e.max_iters:
+            raise ValueError("more iterations than the loss buffer holds")
+        if (e.fit.h, e.fit.w, e.fit.m, e.deterministic, e.fuse_adam, e.model.device) != \
+                (e0.fit.h, e0.fit.w, e0.fit.m, e0.deterministic, e0.fuse_adam, e0.model.device):
+            raise ValueError("batched fits must share shape, movement-group count, device and accumulation mode")
+        e.fit.lr = float(learning_rate)
+    lam = (C.c_float * len(lambdas))(*[float(v) for v in lambdas])
+    fits = (C.POINTER(nat.Fit) * len(engines))(*[C.pointer(e.fit) for e in engines])
+    dev = e0.model.device
+    with torch.cuda.device(dev):
+        nat.check(lib.immoco_fit_run_batched(fits, len(engines), it_begin, it_end, lam,
+                                             torch.cuda.current_stream(dev).cuda_stream, profile, profile_every),
+                  "fit_run_batched")
+    single = lib.immoco_launches_per_iteration_mode(e0.fit.m, int(e0.deterministic), int(e0.fuse_adam))
+    shared = (2 if e0.fit.m > 0 else 1) + 4 + (1 if e0.deterministic else 0)   # MLP fwd, GE, rows x2, colpass(, finalize)
+    per_iter = shared + len(engines) * (single - shared)
+    e0.launches += (it_end - it_begin) * per_iter
+
+
 def imcoco_motion_correction(kspace_corr, masks, iters=200, learning_rate=1e-2, lambda_ge=1e-2,
                              debug=False, *, image_params=None, motion_params=None,
                              kmax: float = 16000.0, variant: str = "main", return_trace: bool = False,

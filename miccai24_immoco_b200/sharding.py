@@ -45,7 +45,7 @@ def gather_images(local: torch.Tensor, n_slices: int, rank: int, world: int, dst
 def reconstruct_slices(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], *, iters: int = 200,
                        learning_rate: float = 1e-2, lambda_ge: float = 1e-2,
                        reconstruct_fn: Optional[Callable] = None, in_flight: Optional[int] = None,
-                       deterministic: Optional[bool] = None) -> Optional[torch.Tensor]:
+                       deterministic: Optional[bool] = None, batch: Optional[int] = None) -> Optional[torch.Tensor]:
     """Reconstruct every slice of a stack, sharded over the ranks of the default process group.
 
     By default each rank runs its shard through ``reconstruct_batch`` (several slices in flight per
@@ -57,10 +57,10 @@ def reconstruct_slices(kspaces: Sequence[torch.Tensor], masks: Sequence[torch.Te
     n = len(kspaces)
     mine = shard_indices(n, rank, world)
     if reconstruct_fn is None:
-        from .batch import DEFAULT_IN_FLIGHT, reconstruct_batch
+        from .batch import DEFAULT_BATCH, DEFAULT_IN_FLIGHT, reconstruct_batch
         outs = reconstruct_batch([kspaces[s] for s in mine], [masks[s] for s in mine], iters, learning_rate,
-                                 lambda_ge, in_flight=in_flight or DEFAULT_IN_FLIGHT,
-                                 deterministic=deterministic) if mine else []
+                                 lambda_ge, in_flight=in_flight or DEFAULT_IN_FLIGHT, deterministic=deterministic,
+                                 batch=batch or DEFAULT_BATCH) if mine else []
     else:
         outs = [reconstruct_fn(kspaces[s], masks[s], iters, learning_rate, lambda_ge, False)[0] for s in mine]
     if outs:

@@ -22,8 +22,13 @@ N_MOV = 4
 def summarize(trace, image_abs, gt_abs):
     trace = np.asarray(trace, dtype=np.float64)
     met = orc.crop_metrics(image_abs.cpu(), gt_abs)
+    # loss spikes: samples more than 3 x the median of their +-25-iteration neighbourhood (Adam at lr 1e-2, no decay)
+    spikes = 0
+    for t in range(100, len(trace)):
+        lo, hi = max(0, t - 25), min(len(trace), t + 26)
+        spikes += int(trace[t] > 3.0 * np.median(trace[lo:hi]))
     return {"tail": float(np.median(trace[-50:])), "last": float(trace[-1]), "max_tail": float(trace[-50:].max()),
-            "spikes": int((trace[200:] > 10.0 * np.median(trace[-50:])).sum()),
+            "spikes": spikes,
             "psnr": float(met["psnr"]), "ssim": float(met["ssim"])}
 
 
@@ -51,10 +56,24 @@ def run_oracle(seed, iters, perturb=0.0):
     return summarize(trace, im.detach().abs(), case["image"].abs())
 
 
-def compare(seeds, iters=1000, modes=("deterministic", "atomic"), log=print):
+def _perturbed(seed, iters, j):
+    """Another 1-ulp perturbation of the SAME slice: different random signs."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    case = orc.make_case(H, W, N_MOV, seed)
+    p_img, p_mot = case_params(seed, DEV)
+    g = torch.Generator(device=DEV).manual_seed(seed + 7919 * j)
+    p_img = p_img * (1.0 + 1e-7 * torch.randn(p_img.shape, device=DEV, generator=g))
+    im, _, trace = orc.imcoco_motion_correction(case["kspace_motion"].to(DEV), case["masks"].to(DEV), iters=iters,
+                                                image_params=p_img, motion_params=p_mot, return_trace=True)
+    return summarize(trace, im.detach().abs(), case["image"].abs())
+
+
+def compare(seeds, iters=1000, modes=("deterministic", "atomic"), log=print, n_perturbed=1):
     rows = []
     for seed in seeds:
         row = {"seed": seed, "oracle": run_oracle(seed, iters), "oracle_perturbed": run_oracle(seed, iters, 1e-7)}
+        for j in range(1, n_perturbed):          # further 1-ulp perturbations (other random signs)
+            row[f"oracle_perturbed{j + 1}"] = _perturbed(seed, iters, j)
         for mode in modes:
             row[mode] = run_ours(seed, iters, mode == "deterministic")
         rows.append(row)

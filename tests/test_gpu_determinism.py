@@ -148,3 +148,87 @@ def test_reconstruct_batch_is_bit_identical_to_single_calls_when_deterministic()
                                                    motion_params=pms[i], return_trace=True, deterministic=True)
         assert torch.equal(imgs[i], im1) and torch.equal(ksp[i], k1), i
         assert np.array_equal(traces[i], tr1), i
+
+
+def _batch_engines(shape, seeds, iters, deterministic):
+    h, w, n_mov = shape
+    engines, lam = [], mb.lambda_schedule(max(iters, 10), 1e-2)[:iters]
+    for seed in seeds:
+        case = orc.make_case(h, w, max(n_mov, 1), seed)
+        p_img, p_mot = case_params(seed, DEV)
+        p_mot = p_mot.clone()
+        p_mot[2048:3072] *= 10.0
+        p_mot[3072:] *= 300.0
+        model = mb.IMMoCo(case["masks"][:n_mov].to(DEV))
+        eng = mb.FitEngine(model, iters, deterministic=deterministic)
+        k = case["kspace_motion"]
+        eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
+        eng.reset(p_img, p_mot)
+        engines.append(eng)
+    return engines, lam
+
+
+def _state(eng, lam):
+    return {"image": eng.image.clone(), "k": eng.k_out.clone(), "params": eng.params.clone(), "m": eng.state[1].clone(),
+            "v": eng.state[2].clone(), "loss": eng.loss[:len(lam)].clone(), "trace": eng.loss_trace(lam).copy()}
+
+
+@pytest.mark.parametrize("shape,n_batch", [((320, 320, 4), 4), ((64, 48, 2), 3), ((640, 368, 5), 2), ((32, 32, 0), 2),
+                                           ((48, 40, 1), 8)])
+def test_batched_fit_is_bit_identical_to_single_fits(shape, n_batch):
+    """immoco_fit_run_batched (instance dimension on the latency-bound kernels): every instance of the batch ends
+    exactly where its own immoco_fit_run puts it -- deterministic mode, so bit for bit -- also when the batch is
+    advanced in several calls."""
+    iters = 10 if shape[0] >= 320 else 16
+    seeds = [30 + i for i in range(n_batch)]
+    singles, lam = _batch_engines(shape, seeds, iters, True)
+    for e in singles:
+        e.run(lam, 1e-2)
+    torch.cuda.synchronize()
+    want = [_state(e, lam) for e in singles]
+    del singles
+    for chunks in ([(0, iters)], [(0, 3), (3, iters)]):
+        batch, _ = _batch_engines(shape, seeds, iters, True)
+        for a, b in chunks:
+            mb.run_batched(batch, lam, 1e-2, a, b)
+        torch.cuda.synchronize()
+        for i, e in enumerate(batch):
+            _assert_identical(_state(e, lam), want[i], f"instance {i} of {n_batch}, chunks {chunks}")
+        del batch
+
+
+def test_batched_fit_atomic_mode_agrees_with_single_fits():
+    shape, iters, seeds = (64, 48, 2), 12, [41, 42, 43, 44]
+    singles, lam = _batch_engines(shape, seeds, iters, False)
+    for e in singles:
+        e.run(lam, 1e-2)
+    batch, _ = _batch_engines(shape, seeds, iters, False)
+    mb.run_batched(batch, lam, 1e-2)
+    torch.cuda.synchronize()
+    for a, b in zip(batch, singles):
+        ta, tb = a.loss_trace(lam), b.loss_trace(lam)
+        rel = np.abs(ta - tb) / np.abs(tb)
+        assert rel[:4].max() < 1e-5 and rel.max() < 5e-3, rel
+    with pytest.raises(ValueError):          # different shapes cannot share a batch
+        other, _ = _batch_engines((48, 40, 2), [50], iters, False)
+        mb.run_batched([batch[0], other[0]], lam, 1e-2)
+
+
+def test_reconstruct_batch_groups_equal_shapes_and_stays_bit_identical():
+    from miccai24_immoco_b200 import reconstruct_batch
+    iters, ks, ms, pis, pms = 12, [], [], [], []
+    shapes = [(64, 48, 2), (48, 40, 1), (64, 48, 2), (64, 48, 2), (48, 40, 1), (64, 48, 3), (64, 48, 2), (64, 48, 2)]
+    for s, (h, w, m) in enumerate(shapes):
+        case = orc.make_case(h, w, m, 60 + s)
+        ks.append(case["kspace_motion"])
+        ms.append(case["masks"][:m])
+        pi, pm = case_params(60 + s)
+        pis.append(pi)
+        pms.append(pm)
+    imgs, ksp, traces = reconstruct_batch(ks, ms, iters, image_params=pis, motion_params=pms, return_kspace=True,
+                                          return_traces=True, deterministic=True, batch=4)
+    for i in range(len(ks)):
+        im1, k1, tr1 = mb.imcoco_motion_correction(ks[i].to(DEV), ms[i].to(DEV), iters=iters, image_params=pis[i],
+                                                   motion_params=pms[i], return_trace=True, deterministic=True)
+        assert torch.equal(imgs[i], im1) and torch.equal(ksp[i], k1), i
+        assert np.array_equal(traces[i], tr1), i

@@ -443,10 +443,15 @@ def test_mlp_backward_partials_are_deterministic_and_sum_to_the_gradient(native_
     assert rel_l2(g_sum[: width * 32], g_at[: width * 32]) < 2e-6
     assert rel_l2(g_sum[width * 32: width * 34], g_at[width * 32: width * 34]) < 2e-6
     assert bool((parts[0][:, width * 34:] == 0).all())               # padded W2 rows are never written
-    # Adam over the blocks (ordered sum inside the kernel) vs Adam over the fp32 ordered sum
-    g_ord = torch.zeros(n_mlp, device=DEV)
+    # Adam over the blocks (fixed summation tree inside the kernel: lane l adds blocks l, l + 32, ... in order,
+    # then a 5-step butterfly) vs Adam over the same tree evaluated with torch fp32 adds
+    lanes = torch.zeros(32, n_mlp, device=DEV)
     for c in range(n_part):
-        g_ord += parts[0][c]
+        lanes[c % 32] += parts[0][c]
+    idx = torch.arange(32, device=DEV)
+    for o in (16, 8, 4, 2, 1):
+        lanes = lanes + lanes[idx ^ o]
+    g_ord = lanes[0].contiguous()
     pa, ma, va = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
     pb, mb_, vb = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
     nat.check(native_lib.immoco_adam_step_partials(pa.data_ptr(), parts[0].data_ptr(), n_part, ma.data_ptr(), va.data_ptr(),

@@ -16,16 +16,18 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=8)
     ap.add_argument("--iters", type=int, default=1000)
+    ap.add_argument("--perturbed", type=int, default=3, help="1-ulp-perturbed oracle runs per slice")
     a = ap.parse_args()
     mb.build()
     t0 = time.time()
-    rows = lu.compare(range(1000, 1000 + a.seeds), iters=a.iters, log=lambda s: print(s, flush=True))
+    rows = lu.compare(range(1000, 1000 + a.seeds), iters=a.iters, log=lambda s: print(s, flush=True), n_perturbed=a.perturbed)
     print(f"[{time.time() - t0:.0f} s]")
-    for mode in ("deterministic", "atomic", "oracle_perturbed"):
+    names = ["deterministic", "atomic", "oracle_perturbed"] + [f"oracle_perturbed{j + 1}" for j in range(1, a.perturbed)]
+    for mode in names:
         for key, rel in (("psnr", False), ("ssim", False), ("tail", True), ("last", True)):
             d = lu.spread(rows, mode, "oracle", key, rel)
             print(f"{mode:17s} vs oracle, {key:4s}{' (relative)' if rel else ''}: median {np.median(d):.4g}  max {d.max():.4g}")
-    for name in ("oracle", "oracle_perturbed", "deterministic", "atomic"):
+    for name in ["oracle"] + names:
         last = np.asarray([r[name]["last"] for r in rows])
         tail = np.asarray([r[name]["tail"] for r in rows])
         print(f"{name:17s}: last-iteration loss min {last.min():.5f} max {last.max():.5f}; tail median min {tail.min():.5f} "
