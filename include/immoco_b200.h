@@ -314,6 +314,15 @@ int immoco_replace_lines(float* k, const float* k_moved, int64_t* mask, const in
  *          NULL) receives the 2x2 average pool (planes, h/2, w/2).  conv1x1: with bias (may be NULL). -- */
 int immoco_unet_conv3x3(const float* in0, int32_t c0, const float* in1, int32_t c1, const float* weight,
                         float* out, double* stats, int32_t n, int32_t cout, int32_t h, int32_t w, void* stream);
+/* The same convolution on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, implicit GEMM over shifted views
+ * of one staged input window): weights packed ONCE per layer by immoco_unet_pack_conv3x3 into w_hi / w_lo
+ * ((cin / 4) * 9 * cout * 4 floats each: [channel quad][tap][cout][4], tf32 hi and lo parts).  Requires
+ * (c0 + c1) % 8 == 0, c0 % 4 == 0, cout % 32 == 0 (IMMOCO_ERR_UNSUPPORTED otherwise: the 2-channel input
+ * layer stays on immoco_unet_conv3x3).  Same outputs / statistics contract. */
+int immoco_unet_pack_conv3x3(const float* weight, float* w_hi, float* w_lo, int32_t cout, int32_t cin, void* stream);
+int immoco_unet_conv3x3_tc(const float* in0, int32_t c0, const float* in1, int32_t c1, const float* w_hi,
+                           const float* w_lo, float* out, double* stats, int32_t n, int32_t cout, int32_t h,
+                           int32_t w, void* stream);
 int immoco_unet_convt2x2(const float* in, const float* weight, float* out, double* stats, int32_t n,
                          int32_t cin, int32_t cout, int32_t h, int32_t w, void* stream);
 int immoco_unet_instnorm_lrelu(float* x, const double* stats, float* pooled, int32_t planes, int32_t h,

@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("IMMOCO_LIB_PATH") or os.path.join(_HERE, "libimmoco_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["hashgrid.cu", "hashgrid_csr.cu", "mlp_tc.cu", "forward_model.cu", "fit.cu", "metrics.cu", "simulate.cu", "unet.cu",
-           "autofocus.cu"]
+           "unet_tc.cu", "autofocus.cu"]
 
 MAX_LEVELS = 16
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -135,6 +135,9 @@ _SIGNATURES = {
     "immoco_replace_lines": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_unet_conv3x3": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, _P]),
+    "immoco_unet_pack_conv3x3": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "immoco_unet_conv3x3_tc": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, _P]),
     "immoco_unet_convt2x2": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_unet_instnorm_lrelu": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
     "immoco_unet_conv1x1": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -5,7 +5,8 @@ src/models/unet.py:17-187 with InstanceNorm2d; used at src/test/test_immoco.py:1
 ``get_unet(in_chans, out_chans, chans, num_pool_layers, drop_prob)`` keeps the reference signature and
 returns a module whose ``state_dict()`` has fastmri's keys and shapes, so
 ``net.load_state_dict(torch.load("kLDNet.pth"))`` works unchanged.  ``forward`` is inference only and runs
-hand-written kernels (csrc/unet.cu): conv3x3 / conv-transpose with fused instance statistics, one
+hand-written kernels (csrc/unet_tc.cu: the 3x3 convolutions as tcgen05 implicit GEMMs with the 3xTF32 split;
+csrc/unet.cu: the 2-channel input layer, conv-transpose, norm, head) with fused instance statistics, one
 normalise + LeakyReLU (+ 2x2 average pool) pass per layer, the channel concat folded into the next
 convolution's loads.  No cuDNN, no eager fallback.
 """
@@ -40,6 +41,8 @@ class Unet(nn.Module):
             raise ValueError("num_pool_layers must be >= 1")
         self.in_chans, self.out_chans, self.chans = in_chans, out_chans, chans
         self.num_pool_layers, self.drop_prob = num_pool_layers, drop_prob
+        self.tensor_cores = True      # 3x3 convolutions on tcgen05 (False: the fp32 SIMT kernels, A/B checks)
+        self._pack_cache: dict = {}
         self._keys: List[str] = []
         # encoder / bottleneck / decoder convolution pairs, in fastmri's registration order
         ch = chans
@@ -81,15 +84,38 @@ class Unet(nn.Module):
         return self.get_parameter(key).detach()
 
     # ---- kernels ------------------------------------------------------------------------------------------
-    @staticmethod
-    def _conv3x3(in0, in1, weight, cout):
+    def _packed(self, key: str):
+        """tf32 hi / lo parts of a 3x3 weight in the tensor-core kernel's [channel quad][tap][cout][4] layout,
+        packed once per parameter version (inference weights are constant)."""
+        p = self.get_parameter(key)
+        tag = (p.data_ptr(), p._version, str(p.device))
+        hit = self._pack_cache.get(key)
+        if hit is None or hit[0] != tag:
+            cout, cin = p.shape[0], p.shape[1]
+            w_hi = torch.empty((cin // 4) * 9 * cout * 4, dtype=torch.float32, device=p.device)
+            w_lo = torch.empty_like(w_hi)
+            nat.check(nat.lib().immoco_unet_pack_conv3x3(p.detach().data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), cout,
+                                                         cin, _stream()), "unet_pack_conv3x3")
+            hit = (tag, w_hi, w_lo)
+            self._pack_cache[key] = hit
+        return hit[1], hit[2]
+
+    def _conv3x3(self, in0, in1, key, cout):
         n, c0, h, w = in0.shape
         c1 = 0 if in1 is None else in1.shape[1]
         out = torch.empty((n, cout, h, w), dtype=torch.float32, device=in0.device)
         stats = torch.zeros((n, cout, 2), dtype=torch.float64, device=in0.device)
-        nat.check(nat.lib().immoco_unet_conv3x3(in0.data_ptr(), c0, 0 if in1 is None else in1.data_ptr(), c1,
-                                                weight.data_ptr(), out.data_ptr(), stats.data_ptr(), n, cout, h, w,
-                                                _stream()), "unet_conv3x3")
+        in1_ptr = 0 if in1 is None else in1.data_ptr()
+        if self.tensor_cores and (c0 + c1) % 8 == 0 and c0 % 4 == 0 and cout % 32 == 0:
+            # tcgen05 implicit GEMM (csrc/unet_tc.cu); the 2-channel input layer below stays SIMT
+            w_hi, w_lo = self._packed(key)
+            nat.check(nat.lib().immoco_unet_conv3x3_tc(in0.data_ptr(), c0, in1_ptr, c1, w_hi.data_ptr(), w_lo.data_ptr(),
+                                                       out.data_ptr(), stats.data_ptr(), n, cout, h, w, _stream()),
+                      "unet_conv3x3_tc")
+        else:
+            nat.check(nat.lib().immoco_unet_conv3x3(in0.data_ptr(), c0, in1_ptr, c1, self._p(key).data_ptr(),
+                                                    out.data_ptr(), stats.data_ptr(), n, cout, h, w, _stream()),
+                      "unet_conv3x3")
         return out, stats
 
     @staticmethod
@@ -103,9 +129,9 @@ class Unet(nn.Module):
 
     def _block(self, in0, in1, keys, pool: bool):
         k0, k1, cout = keys
-        a, st = self._conv3x3(in0, in1, self._p(k0), cout)
+        a, st = self._conv3x3(in0, in1, k0, cout)
         self._norm_act(a, st, False)
-        b, st = self._conv3x3(a, None, self._p(k1), cout)
+        b, st = self._conv3x3(a, None, k1, cout)
         pooled = self._norm_act(b, st, pool)
         return b, pooled
 

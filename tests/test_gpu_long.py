@@ -1,15 +1,21 @@
 """GPU, slow: the headline configuration run to completion (C2: 320x320, n_M=4, 1000 iterations) against
 the oracle loop on the same GPU, over several slices, in both accumulation modes.
 
-What is asserted (BASELINE.json north_star asks for final PSNR within 0.1 dB / SSIM within 0.002 "after a
-fixed iteration count"): the loop is chaotic, so the yardstick is the oracle against ITSELF under a 1-ulp
-perturbation of its initial parameters, measured in the same run on the same slices:
-  * final PSNR / SSIM: median over slices of |ours - oracle| <= max(0.1 dB, 2 x the oracle's own median
-    self-difference) / max(0.002, 2 x ...), and no slice further out than max(3 x the oracle's worst
-    self-difference, 0.5 dB / 0.01);
-  * tail loss (median of the last 50 iterations): same rule on the relative difference, floor 1e-3;
-  * every run ends on a finite loss far below the first iteration's.
-IMMOCO_LONG_SEEDS (default 4) slices; tools/long_run_stats.py writes the 8-slice table kept under profiles/."""
+BASELINE.json's north_star asks for final PSNR within 0.1 dB / SSIM within 0.002 "after a fixed iteration
+count".  The loop is chaotic: the ORACLE ITSELF, re-run with a 1-ulp perturbation of its initial parameters,
+ends 0.7 - 0.9 dB away from its own unperturbed run in the median (max 2.8 dB over 8 slices x 3 perturbations,
+profiles/round2_long_runs.txt), and one run in eight ends its last iteration on one of Adam's loss spikes (last
+loss 0.2 ... 2.5 against a tail of 0.002 - 0.005).  A 1000-iteration comparison can therefore only be
+statistical, with the oracle's own self-difference, measured in the same run on the same slices, as yardstick:
+  * final PSNR / SSIM: median over slices of |ours - oracle| <= max(0.1 dB, 2.5 x the pooled median of the
+    oracle's self-differences) / max(0.002, 2.5 x ...); no slice further out than max(0.5 dB, 2.5 x the worst
+    self-difference) / max(0.01, ...);
+  * tail loss (median of the last 50 iterations): the same median rule on the relative difference (floor
+    1e-3), and every run's tail within 20 x the oracle's;
+  * every run ends on a finite loss.
+Both sides are random draws (torch's index_add_ / grid_sample backward on CUDA are atomic too), hence the
+factors.  IMMOCO_LONG_SEEDS (default 4) slices x IMMOCO_LONG_PERTURBED (default 2) oracle perturbations;
+tools/long_run_stats.py writes the 8-slice table kept under profiles/."""
 import os
 
 import numpy as np
@@ -24,15 +30,18 @@ pytestmark = [pytest.mark.gpu, pytest.mark.slow]
 def test_c2_1000_iterations_against_oracle_distribution():
     mb.build()
     n = int(os.environ.get("IMMOCO_LONG_SEEDS", "4"))
-    rows = lu.compare(range(1000, 1000 + n), iters=1000)
+    n_pert = int(os.environ.get("IMMOCO_LONG_PERTURBED", "2"))
+    rows = lu.compare(range(1000, 1000 + n), iters=1000, n_perturbed=n_pert)
+    pert = ["oracle_perturbed"] + [f"oracle_perturbed{j + 1}" for j in range(1, n_pert)]
     for mode in ("deterministic", "atomic"):
         for key, floor_med, floor_max, rel in (("psnr", 0.1, 0.5, False), ("ssim", 0.002, 0.01, False),
-                                               ("tail", 1e-3, 0.5, True)):
+                                               ("tail", 1e-3, None, True)):
             ours = lu.spread(rows, mode, "oracle", key, rel)
-            self_ = lu.spread(rows, "oracle_perturbed", "oracle", key, rel)
+            self_ = np.concatenate([lu.spread(rows, p, "oracle", key, rel) for p in pert])
             print(f"{mode:13s} {key:4s}: |ours - oracle| median {np.median(ours):.4g} max {ours.max():.4g}; "
-                  f"oracle self-difference median {np.median(self_):.4g} max {self_.max():.4g}")
-            assert np.median(ours) <= max(floor_med, 2.0 * np.median(self_)), (mode, key, ours, self_)
-            assert ours.max() <= max(floor_max, 3.0 * self_.max()), (mode, key, ours, self_)
+                  f"oracle self-difference (pooled, {self_.size} runs) median {np.median(self_):.4g} max {self_.max():.4g}")
+            assert np.median(ours) <= max(floor_med, 2.5 * np.median(self_)), (mode, key, ours, self_)
+            if floor_max is not None:
+                assert ours.max() <= max(floor_max, 2.5 * self_.max()), (mode, key, ours, self_)
         for r in rows:
-            assert np.isfinite(r[mode]["last"]) and r[mode]["tail"] < 1.0, r
+            assert np.isfinite(r[mode]["last"]) and r[mode]["tail"] <= 20.0 * r["oracle"]["tail"], r
