@@ -148,6 +148,69 @@ def test_unet_full_size_matches_oracle(n, h, w):
     assert rel_l2(y, want) < 5e-5
 
 
+@pytest.mark.parametrize("n,c0,c1,cout,h,w", [(2, 32, 0, 32, 48, 40), (1, 64, 64, 64, 40, 40), (3, 32, 0, 64, 20, 20),
+                                              (1, 256, 256, 256, 24, 16), (2, 512, 0, 512, 20, 20), (1, 32, 32, 32, 320, 320),
+                                              (1, 8, 0, 96, 17, 9)])
+def test_conv3x3_tensor_core_kernel_matches_torch(native_lib, n, c0, c1, cout, h, w):
+    """immoco_unet_conv3x3_tc (tcgen05 implicit GEMM, 3xTF32) vs F.conv2d fp32 and vs the fp32 SIMT kernel: raw
+    output, instance statistics, channel concat, partial tiles, long channel loops (accumulator flushes)."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from miccai24_immoco_b200 import _native as nat
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(c0 + cout + h)
+    x0 = torch.randn(n, c0, h, w, generator=g).to(DEV)
+    x1 = torch.randn(n, c1, h, w, generator=g).to(DEV) if c1 else None
+    cin = c0 + c1
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)).to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    w_hi = torch.empty((cin // 4) * 9 * cout * 4, device=DEV)
+    w_lo = torch.empty_like(w_hi)
+    nat.check(native_lib.immoco_unet_pack_conv3x3(wt.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), cout, cin, s), "pack")
+    out = torch.full((n, cout, h, w), float("nan"), device=DEV)
+    stats = torch.zeros(n, cout, 2, dtype=torch.float64, device=DEV)
+    nat.check(native_lib.immoco_unet_conv3x3_tc(x0.data_ptr(), c0, 0 if x1 is None else x1.data_ptr(), c1, w_hi.data_ptr(),
+                                                w_lo.data_ptr(), out.data_ptr(), stats.data_ptr(), n, cout, h, w, s), "conv_tc")
+    xin = x0 if x1 is None else torch.cat([x0, x1], 1)
+    want = F.conv2d(xin.double(), wt.double(), padding=1)
+    ref32 = F.conv2d(xin, wt, padding=1)
+    err, floor = rel_l2(out, want), rel_l2(ref32, want)
+    print(f"conv3x3_tc {n}x{cin}->{cout} {h}x{w}: rel-L2 vs fp64 {err:.2e} (cuDNN fp32: {floor:.2e})")
+    assert bool(torch.isfinite(out).all()) and err < max(5e-6, 3.0 * floor)
+    # sums of the (rounded) fp32 outputs, accumulated in fp64: errors relative to sum |x| (the plain sum cancels)
+    assert float(((stats[..., 0] - want.sum((2, 3))).abs() / want.abs().sum((2, 3))).max()) < 1e-6
+    assert rel_l2(stats[..., 1], (want * want).sum((2, 3))) < 1e-5
+    # the SIMT kernel on the same inputs
+    out_s = torch.empty_like(out)
+    stats_s = torch.zeros_like(stats)
+    nat.check(native_lib.immoco_unet_conv3x3(x0.data_ptr(), c0, 0 if x1 is None else x1.data_ptr(), c1, wt.data_ptr(),
+                                             out_s.data_ptr(), stats_s.data_ptr(), n, cout, h, w, s), "conv_simt")
+    assert rel_l2(out, out_s) < 5e-6
+
+
+def test_conv3x3_tensor_core_rejects_unsupported(native_lib):
+    from miccai24_immoco_b200 import _native as nat
+    z = torch.zeros(16, device=DEV)
+    p = z.data_ptr()
+    s = torch.cuda.current_stream().cuda_stream
+    assert native_lib.immoco_unet_conv3x3_tc(p, 2, 0, 0, p, p, p, p, 1, 32, 8, 8, s) == nat.ERR_UNSUPPORTED     # cin = 2
+    assert native_lib.immoco_unet_conv3x3_tc(p, 8, 0, 0, p, p, p, p, 1, 24, 8, 8, s) == nat.ERR_UNSUPPORTED     # cout % 32
+    assert native_lib.immoco_unet_conv3x3_tc(p, 8, 0, 0, p, p, p, p, 0, 32, 8, 8, s) == 0                       # empty batch
+
+
+def test_unet_tensor_core_path_equals_simt_path():
+    """The whole network with the 3x3 convolutions on tcgen05 vs on the fp32 SIMT kernels (A/B switch)."""
+    state = ko.init_unet_state(5)
+    net = mb.get_unet(2, 1, 32, 4, 0.0)
+    net.load_state_dict(state)
+    net = net.cuda()
+    x = torch.randn(2, 2, 96, 80, generator=torch.Generator().manual_seed(1)).to(DEV)
+    y_tc = net(x)
+    net.tensor_cores = False
+    y_simt = net(x)
+    assert rel_l2(y_tc, y_simt) < 2e-5
+
+
 def test_kld_net_to_movement_groups_pipeline():
     """test_immoco.py:47-61 end to end: k-space -> network input -> logits -> mask -> column vote ->
     groups, against the oracle's restatement on the same seeded weights; then the fit accepts them."""

@@ -15,6 +15,9 @@ for n, h, w in ((1, 320, 320), (16, 320, 320), (64, 320, 320), (16, 640, 368)):
         e0.record()
         for _ in range(reps): fn()
         e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / reps
-    ours = t(lambda: net(x)); ref = t(lambda: ko.unet_forward(sd, x))
+    net.tensor_cores = True; ours = t(lambda: net(x))
+    net.tensor_cores = False; simt = t(lambda: net(x)); net.tensor_cores = True
+    ref = t(lambda: ko.unet_forward(sd, x))
     gf = 37.7e9 * n * (h * w) / (320 * 320)
-    print(f"{n:3d} x {h}x{w}: ours {ours:8.2f} ms ({gf/ours/1e9:6.1f} TFLOP/s fp32)   torch/cuDNN fp32 {ref:8.2f} ms", flush=True)
+    print(f"{n:3d} x {h}x{w}: tcgen05 3xTF32 {ours:8.2f} ms ({gf/ours/1e9:6.1f} TFLOP/s fp32-equivalent)   fp32 SIMT {simt:8.2f} ms   "
+          f"torch/cuDNN fp32 {ref:8.2f} ms", flush=True)
