@@ -580,6 +580,15 @@ def run_c4(args):
     e1.record()
     torch.cuda.synchronize()
     kld_ms = e0.elapsed_time(e1) / 3
+    x_in = mb.kld_net_input(k_dev)
+    net(x_in)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        net(x_in)
+    e1.record()
+    torch.cuda.synchronize()
+    unet_ms = e0.elapsed_time(e1) / 3
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -619,7 +628,10 @@ def run_c4(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg, "clocks": clocks,
         "kld_net": {"ms_per_batch": round(kld_ms, 3), "slices_per_s": round(batch / (kld_ms * 1e-3), 1),
-                    "tflops": round(flops / (kld_ms * 1e-3) / 1e12, 2), "weights": "seeded random (kLDNet.pth unavailable)",
+                    "what": "k-space -> network input -> U-Net -> sigmoid / column vote -> movement-group masks of the batch",
+                    "unet_ms_per_batch": round(unet_ms, 3), "unet_tflops_fp32_equivalent": round(flops / (unet_ms * 1e-3) / 1e12, 2),
+                    "unet_kernels": "3x3 convolutions: tcgen05 kind::tf32, 3xTF32 split (csrc/unet_tc.cu)",
+                    "weights": "seeded random (kLDNet.pth unavailable)",
                     "groups_found_first_slices": [int(m.shape[0]) for m in masks_net[:8]]},
         "e2e": {"value": round(n_e2e * batch / e2e_s, 4), "unit": "slices/s", "steps": n_e2e,
                 "h2d_bytes_per_step": int(k_host.numel() * 8 + sum(m.numel() * 8 for m in sim_masks)),

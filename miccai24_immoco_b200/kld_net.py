@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nat
-from .motion_utils import extract_movement_groups
+from .motion_utils import extract_movement_groups, movement_group_labels  # noqa: F401
 from .ops import IFFT, _need_cuda, _stream
 
 _EPS, _SLOPE = 1e-5, 0.2
@@ -198,7 +198,15 @@ def detect_motion_lines(net: Unet, kspace: torch.Tensor) -> torch.Tensor:
 
 def movement_masks_from_kspace(net: Unet, kspace: torch.Tensor) -> List[torch.Tensor]:
     """kld-net -> movement groups for every slice of a (B, H, W) stack: the (M_b, H, W) int64 mask lists
-    ``IMMoCo`` / ``reconstruct_batch`` take.  One host synchronisation per slice (M_b sizes the output)."""
+    ``IMMoCo`` / ``reconstruct_batch`` take (what ``extract_movement_groups(lines[b], make_list=True)`` returns
+    per slice).  The run labelling is one batched pass and ONE host synchronisation for the whole stack (the
+    group counts size the outputs)."""
     lines = detect_motion_lines(net, kspace)
-    h = kspace.shape[-2]
-    return [extract_movement_groups(lines[b], make_list=True, height=h) for b in range(lines.shape[0])]
+    labels = movement_group_labels(lines)                       # (B, W)
+    counts = labels.max(dim=1).values.cpu().tolist() if labels.shape[1] else [0] * labels.shape[0]
+    h, w = kspace.shape[-2], labels.shape[1]
+    out = []
+    for b, m in enumerate(counts):
+        ids = torch.arange(1, m + 1, device=labels.device, dtype=torch.long).view(m, 1, 1)
+        out.append((labels[b].view(1, 1, w).expand(1, h, w) == ids).to(torch.long))
+    return out

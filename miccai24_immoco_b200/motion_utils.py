@@ -35,15 +35,7 @@ def extract_movement_groups(motionline_indcies: torch.Tensor, make_list: bool = 
     if w == 0:
         shape = (0, h, 0) if make_list else (h, 0)
         return torch.zeros(shape, dtype=torch.long, device=dev)
-    is1 = x == 1
-    is0 = x == 0
-    nxt1 = torch.cat([is1[1:], torch.ones(1, dtype=torch.bool, device=dev)])    # last line: no test
-    nxt0 = torch.cat([is0[1:], torch.zeros(1, dtype=torch.bool, device=dev)])
-    labelled = is1 & (nxt1 | nxt0)
-    run_end = is1 & nxt0
-    # label of line i = 1 + number of run ends strictly before i
-    before = torch.cumsum(run_end.to(torch.long), 0) - run_end.to(torch.long)
-    labels = (before + 1) * labelled.to(torch.long)
+    labels = movement_group_labels(x)
     groups = labels.unsqueeze(0).expand(h, w).contiguous()
     if not make_list:
         return groups
@@ -53,6 +45,22 @@ def extract_movement_groups(motionline_indcies: torch.Tensor, make_list: bool = 
     n = int(present[1:].sum().item())
     ids = torch.arange(1, n + 1, device=dev, dtype=torch.long).view(n, 1, 1)
     return (groups.unsqueeze(0) == ids).to(torch.long)
+
+
+def movement_group_labels(flags: torch.Tensor) -> torch.Tensor:
+    """Run labels of per-line flags along the LAST dim ((W,) or (B, W)): 0 = static, 1..M = group, with the
+    element tests of ``extract_movement_groups`` (motion_utils.py:56-109).  Labels are consecutive, so the
+    number of groups of a slice is its largest label."""
+    is1 = flags == 1
+    is0 = flags == 0
+    pad = flags.shape[:-1] + (1,)
+    dev = flags.device
+    nxt1 = torch.cat([is1[..., 1:], torch.ones(pad, dtype=torch.bool, device=dev)], dim=-1)    # last line: no test
+    nxt0 = torch.cat([is0[..., 1:], torch.zeros(pad, dtype=torch.bool, device=dev)], dim=-1)
+    labelled = is1 & (nxt1 | nxt0)
+    run_end = (is1 & nxt0).to(torch.long)
+    before = torch.cumsum(run_end, -1) - run_end        # run ends strictly before line i
+    return (before + 1) * labelled.to(torch.long)
 
 
 def lines_from_mask(mask: torch.Tensor) -> torch.Tensor:
