@@ -227,6 +227,22 @@ def roofline_block(nat, ms_sum, n_prof, h, w, m, n_par2, t_img, t_mot, ms_per_it
     except Exception:
         pass
     b_iter = 28.0 * n_par + 16.0 * (t_img + t_mot) + 64.0 * p * (m + 1)
+    # the hash-grid kernels against the roofline that actually binds them: L2 random 8-byte accesses, peaks measured
+    # on this pool by tools/l2_peaks.cu; accesses = points x 2^D corners x 16 levels per launch
+    l2 = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "round2_l2_peaks.json")) as f:
+            pk = json.load(f)
+        l2 = {"unit": "G table rows / s (one row = 8 bytes = one 32-byte L2 sector)", "source": "profiles/round2_l2_peaks.json"}
+        for slot, taps, key in (("hashgrid_fwd_motion", m * p * 8 * 16, "gather_8B_pair_same_line_Gps"),
+                                ("hashgrid_bwd_motion", m * p * 8 * 16, "red_f32x2_pair_same_slot_Gps"),
+                                ("hashgrid_fwd_image", p * 4 * 16, "gather_8B_pair_same_line_Gps"),
+                                ("hashgrid_bwd_image", p * 4 * 16, "red_f32x2_pair_same_slot_Gps")):
+            if per_slot.get(slot):
+                ach = taps / (per_slot[slot] * 1e-3) / 1e9
+                l2[slot] = {"achieved": round(ach, 1), "peak": pk[key], "frac": round(ach / pk[key], 3), "peak_pattern": key}
+    except Exception:
+        pass
     return {
         "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
@@ -237,6 +253,7 @@ def roofline_block(nat, ms_sum, n_prof, h, w, m, n_par2, t_img, t_mot, ms_per_it
                            for k, v in per_slot.items() if v > 0},
         "instrumented_iterations": n_prof,
         "limiter": LIMITERS.get(dom, ""),
+        "l2": l2,
         "iteration": {"algorithmic_bytes": b_iter, "achieved": round(b_iter / (ms_per_iter * 1e-3) / 1e9, 1),
                       "frac": round(b_iter / (ms_per_iter * 1e-3) / 1e9 / peak, 4)},
     }

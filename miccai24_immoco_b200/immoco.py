@@ -153,10 +153,11 @@ class _ForwardModelFunction(torch.autograd.Function):
         c_tmp = torch.empty((h, w, 2), dtype=torch.float32, device=dev)
         k = torch.empty((h, w, 2), dtype=torch.float32, device=dev)
         lines = model._lines.struct()
-        nat.check(lib.immoco_forward_model(image_ri.data_ptr(), disp.data_ptr(), model._ident.data_ptr(),
-                                           C.byref(lines), twiddle_table(h, dev).data_ptr(),
-                                           twiddle_table(w, dev).data_ptr(), c_tmp.data_ptr(),
-                                           k.data_ptr(), h, w, _stream()), "forward_model")
+        with torch.cuda.device(dev):
+            nat.check(lib.immoco_forward_model(image_ri.data_ptr(), disp.data_ptr(), model._ident.data_ptr(),
+                                               C.byref(lines), twiddle_table(h, dev).data_ptr(),
+                                               twiddle_table(w, dev).data_ptr(), c_tmp.data_ptr(),
+                                               k.data_ptr(), h, w, _stream(dev)), "forward_model")
         ctx.save_for_backward(image_ri, disp)
         ctx.model = model
         return k
@@ -173,12 +174,13 @@ class _ForwardModelFunction(torch.autograd.Function):
         d_image = torch.zeros_like(image_ri)
         d_disp = torch.zeros_like(disp)
         lines = model._lines.struct()
-        nat.check(lib.immoco_forward_model_bwd(d_k.data_ptr(), image_ri.data_ptr(), disp.data_ptr(),
-                                               model._ident.data_ptr(), C.byref(lines),
-                                               twiddle_table(h, dev).data_ptr(),
-                                               twiddle_table(w, dev).data_ptr(), c_tmp.data_ptr(),
-                                               d_image.data_ptr(), d_disp.data_ptr(), 0, h, w, _stream()),
-                  "forward_model_bwd")
+        with torch.cuda.device(dev):
+            nat.check(lib.immoco_forward_model_bwd(d_k.data_ptr(), image_ri.data_ptr(), disp.data_ptr(),
+                                                   model._ident.data_ptr(), C.byref(lines),
+                                                   twiddle_table(h, dev).data_ptr(),
+                                                   twiddle_table(w, dev).data_ptr(), c_tmp.data_ptr(),
+                                                   d_image.data_ptr(), d_disp.data_ptr(), 0, h, w, _stream(dev)),
+                      "forward_model_bwd")
         return d_image, d_disp, None
 
 

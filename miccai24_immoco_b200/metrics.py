@@ -11,6 +11,8 @@ on the acceptance path (BASELINE.json names PSNR / SSIM) and is returned as NaN.
 from __future__ import annotations
 
 import numpy as np
+import warnings
+
 import torch
 
 from . import _native as nat
@@ -71,6 +73,9 @@ def metric_sums(pred_recon: torch.Tensor, gt_recon: torch.Tensor, kernel_size: i
     return acc
 
 
+_HAARPSI_WARNED = False
+
+
 def calmetric2D(pred_recon: torch.Tensor, gt_recon: torch.Tensor):
     """(psnr, ssim, haar_psi, rmse) of (B, 1, H, W) reconstructions (evaluate.py:57-80): both inputs are
     min-max normalised per image, PSNR with data_range 1, SSIM 11x11 Gaussian, all 'mean' reductions."""
@@ -86,6 +91,13 @@ def calmetric2D(pred_recon: torch.Tensor, gt_recon: torch.Tensor):
     psnr = (20 * torch.log10(1.0 / torch.sqrt(mse))).mean().float()
     ssim = (acc[:, 1] / acc[:, 2]).mean().float()
     rmse_all = torch.sqrt(acc[:, 0].sum() / (n_px * acc.shape[0])).float()
+    # HaarPSI (piq.haarpsi at evaluate.py:72) is NOT implemented on this path: the third return value is NaN.  A
+    # caller that aggregates it like the reference's tables (test_immoco.py:77-85) must drop that column; warn once.
+    global _HAARPSI_WARNED
+    if not _HAARPSI_WARNED:
+        warnings.warn("miccai24_immoco_b200.calmetric2D: HaarPSI is not implemented on the CUDA path; the third "
+                      "returned value is NaN (PSNR, SSIM and RMSE are computed)", RuntimeWarning, stacklevel=2)
+        _HAARPSI_WARNED = True
     haar = torch.full((), float("nan"), device=acc.device)
     return psnr, ssim, haar, rmse_all
 

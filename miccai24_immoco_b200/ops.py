@@ -17,8 +17,9 @@ from . import _native as nat
 from .encoding import GridSpec, MlpSpec, grid_spec, mlp_spec, twiddles, OUT_PAD, N_ENCODED
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    """Raw handle of torch's current stream on ``device`` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _need_cuda(t: torch.Tensor, what: str) -> None:
@@ -70,9 +71,10 @@ class _InrFunction(torch.autograd.Function):
         w1 = p.data_ptr()
         w2 = w1 + 4 * mlp.n_w1
         table = w1 + 4 * mlp.n_params
-        s = _stream()
-        nat.check(lib.immoco_hashgrid_fwd(grid_desc, x.data_ptr(), table, enc.data_ptr(), n, s), "hashgrid_fwd")
-        nat.check(lib.immoco_mlp_fwd(enc.data_ptr(), w1, w2, out.data_ptr(), n, mlp.width, mlp.act, 0, s), "mlp_fwd")
+        with torch.cuda.device(x.device):       # the library launches on the CURRENT device: make it the tensors'
+            s = _stream(x.device)
+            nat.check(lib.immoco_hashgrid_fwd(grid_desc, x.data_ptr(), table, enc.data_ptr(), n, s), "hashgrid_fwd")
+            nat.check(lib.immoco_mlp_fwd(enc.data_ptr(), w1, w2, out.data_ptr(), n, mlp.width, mlp.act, 0, s), "mlp_fwd")
         ctx.save_for_backward(x, params, enc)
         ctx.grid_desc, ctx.mlp, ctx.n_out = grid_desc, mlp, n_out
         return out[:, :n_out]
@@ -93,10 +95,11 @@ class _InrFunction(torch.autograd.Function):
         g1 = grads.data_ptr()
         g2 = g1 + 4 * mlp.n_w1
         gt = g1 + 4 * mlp.n_params
-        s = _stream()
-        nat.check(lib.immoco_mlp_bwd(enc.data_ptr(), w1, w2, d_out.data_ptr(), d_enc.data_ptr(), g1, g2, n,
-                                     mlp.width, mlp.act, s), "mlp_bwd")
-        nat.check(lib.immoco_hashgrid_bwd(ctx.grid_desc, x.data_ptr(), d_enc.data_ptr(), gt, n, s), "hashgrid_bwd")
+        with torch.cuda.device(x.device):
+            s = _stream(x.device)
+            nat.check(lib.immoco_mlp_bwd(enc.data_ptr(), w1, w2, d_out.data_ptr(), d_enc.data_ptr(), g1, g2, n,
+                                         mlp.width, mlp.act, s), "mlp_bwd")
+            nat.check(lib.immoco_hashgrid_bwd(ctx.grid_desc, x.data_ptr(), d_enc.data_ptr(), gt, n, s), "hashgrid_bwd")
         return None, grads, None, None, None
 
 
@@ -156,10 +159,11 @@ def _fft2c_raw(x: torch.Tensor, inverse: bool, scale: float) -> torch.Tensor:
     batch = xr.numel() // (h * w * 2) if h * w > 0 else 0
     out = torch.empty_like(xr)
     tmp = torch.empty_like(xr)
-    nat.check(nat.lib().immoco_fft2c(xr.data_ptr(), out.data_ptr(), tmp.data_ptr(), batch, h, w,
-                                     twiddle_table(h, x.device).data_ptr(),
-                                     twiddle_table(w, x.device).data_ptr(), 1 if inverse else 0,
-                                     float(scale), _stream()), "fft2c")
+    with torch.cuda.device(x.device):
+        nat.check(nat.lib().immoco_fft2c(xr.data_ptr(), out.data_ptr(), tmp.data_ptr(), batch, h, w,
+                                         twiddle_table(h, x.device).data_ptr(),
+                                         twiddle_table(w, x.device).data_ptr(), 1 if inverse else 0,
+                                         float(scale), _stream(x.device)), "fft2c")
     return torch.view_as_complex(out)
 
 
@@ -201,8 +205,9 @@ class _GradEntropyFunction(torch.autograd.Function):
         h, w = x.shape
         acc = torch.zeros(1, dtype=torch.float64, device=x.device)
         grad = torch.empty_like(xr)
-        nat.check(nat.lib().immoco_grad_entropy(xr.data_ptr(), 1.0, acc.data_ptr(), grad.data_ptr(), 0,
-                                                h, w, _stream()), "grad_entropy")
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().immoco_grad_entropy(xr.data_ptr(), 1.0, acc.data_ptr(), grad.data_ptr(), 0,
+                                                    h, w, _stream(x.device)), "grad_entropy")
         ctx.save_for_backward(grad)
         return acc[0].float()
 

@@ -232,3 +232,28 @@ def test_reconstruct_batch_groups_equal_shapes_and_stays_bit_identical():
                                                    motion_params=pms[i], return_trace=True, deterministic=True)
         assert torch.equal(imgs[i], im1) and torch.equal(ksp[i], k1), i
         assert np.array_equal(traces[i], tr1), i
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process_gives_the_same_bits():
+    """launch attributes (dynamic shared-memory opt-in) and the SM count are per device, and the
+    native calls must run on the tensors' device whatever the current device is.  A fit on cuda:1, issued while
+    cuda:0 is current and after cuda:0 has used every kernel, must equal the fit on cuda:0 bit for bit
+    (deterministic mode); module-mode operators are exercised on cuda:1 too."""
+    case = orc.make_case(64, 48, 2, 11)
+    p_img, p_mot = case_params(11)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)                      # current device stays cuda:0 throughout
+        im, k, tr = mb.imcoco_motion_correction(case["kspace_motion"].to(dev), case["masks"].to(dev), iters=12,
+                                                image_params=p_img.to(dev), motion_params=p_mot.to(dev),
+                                                return_trace=True, deterministic=True)
+        torch.cuda.synchronize(dev)
+        outs.append((im.cpu(), k.cpu(), tr))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    x = torch.randn(64, 48, dtype=torch.complex64, device="cuda:1")
+    assert rel_l2(mb.IFFT(mb.FFT(x)), x) < 2e-6
+    model = mb.IMMoCo(case["masks"].to("cuda:1"))
+    kf, img = model()
+    assert kf.device.index == 1 and bool(torch.isfinite(torch.view_as_real(kf)).all())
