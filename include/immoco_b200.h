@@ -142,6 +142,20 @@ int immoco_mlp_bwd_partials(const float* enc, const float* w1, const float* w2, 
                             float* d_enc, float* g_part, int64_t n_points, int32_t width, int32_t act,
                             void* stream);
 int immoco_mlp_bwd_partial_count(int64_t n_points);
+/* 64-wide network over a 3-D hash grid (the Motion INR, src/models/immoco.py:19-25,64-65): immoco_mlp_bwd with the
+ * table gradients of the hashed levels reduced straight from the dE tile inside the kernel (lane pairs = the two
+ * dim-0 corners of a point, same arithmetic as immoco_hashgrid_bwd) -- no feature-plane round trip for those
+ * levels.  d_enc receives the DENSE levels only; immoco_hashgrid_bwd_dense_levels finishes them.  Together the two
+ * calls equal immoco_mlp_bwd + immoco_hashgrid_bwd up to the order of the float atomics. */
+int immoco_mlp_bwd_scatter(const float* enc, const float* w1, const float* w2, const float* d_out,
+                           float* d_enc, float* g_w1, float* g_w2, const immoco_grid_desc* grid,
+                           const float* coords, float* grad_table, int64_t n_points, int32_t width,
+                           int32_t act, void* stream);
+int immoco_hashgrid_bwd_dense_levels(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
+                                     float* grad_table, int64_t n_points, void* stream);
+/* 1: immoco_fit_run uses the pair above for the motion branch of the float-atomic path; 0: separate kernels. */
+int immoco_set_fused_scatter(int32_t on);
+int immoco_get_fused_scatter(void);
 /* (The fp32 SIMT A/B kernels of round 1 are no longer part of this library: they are built into the
  * test-side checker tests/checkers/_mlp_simt.so.  The product MLPs are tcgen05 kind::tf32, 3xTF32 split,
  * accumulators in TMEM.) */

@@ -102,6 +102,11 @@ _SIGNATURES = {
     "immoco_hashgrid_bwd_csr_adam": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P, _P, _P, C.c_double,
                                                C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
     "immoco_mlp_bwd_partials": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "immoco_mlp_bwd_scatter": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(GridDesc), _P, _P, C.c_int64, C.c_int32,
+                                         C.c_int32, _P]),
+    "immoco_hashgrid_bwd_dense_levels": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, _P]),
+    "immoco_set_fused_scatter": (C.c_int, [C.c_int32]),
+    "immoco_get_fused_scatter": (C.c_int, []),
     "immoco_mlp_bwd_partial_count": (C.c_int, [C.c_int64]),
     "immoco_adam_step_partials": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double,
                                             C.c_double, C.c_int32, _P]),

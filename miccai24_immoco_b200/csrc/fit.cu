@@ -163,6 +163,13 @@ AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, int 
   return a;
 }
 
+// 1: the float-atomic path reduces the motion grid's hashed-level gradients inside the 64-wide MLP backward
+// kernel (immoco_mlp_bwd_scatter); 0: separate scatter kernel over the feature planes.  Default set from the
+// measurement in profiles/round2_fused_scatter.txt
+static int g_fused_scatter = 0;
+extern "C" int immoco_set_fused_scatter(int32_t on) { g_fused_scatter = on ? 1 : 0; return 0; }
+extern "C" int immoco_get_fused_scatter(void) { return g_fused_scatter; }
+
 static int g_deterministic = 0;
 extern "C" int immoco_set_deterministic(int32_t on) { g_deterministic = on ? 1 : 0; return 0; }
 extern "C" int immoco_get_deterministic(void) { return g_deterministic; }
@@ -648,10 +655,21 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
       if (ev) cudaEventRecord(ev[2 + 2 * 15], (cudaStream_t)is);
       continue;
     }
-    K(10, ms, M > 0 ? EACH(immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
-                                          gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream)) : nop());
-    if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
-    K(11, ms, M > 0 ? EACH(immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream)) : nop());
+    if (g_fused_scatter && M > 0 && wm == 64) {
+      // the hashed levels' table gradients leave the MLP backward kernel directly (no feature-plane round trip);
+      // the dense levels follow through d_enc
+      K(10, ms, EACH(immoco_mlp_bwd_scatter(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
+                                            gm + (int64_t)wm * 32, &f->grid_motion, f->coords_motion, gm + mlp_m, MP, wm,
+                                            f->act_motion, stream)));
+      if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
+      K(11, ms, EACH(immoco_hashgrid_bwd_dense_levels(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP,
+                                                      stream)));
+    } else {
+      K(10, ms, M > 0 ? EACH(immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
+                                            gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream)) : nop());
+      if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
+      K(11, ms, M > 0 ? EACH(immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream)) : nop());
+    }
     K(12, is, EACH(immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
                                   gi + (int64_t)wi * 32, P, wi, f->act_image, is)));
     K(13, is, EACH(immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is)));

@@ -7,6 +7,7 @@
 // Grid = (point tiles, levels): CTAs of one level are adjacent in launch order, so one level's
 // table (<= 4 MB) is the L2 working set at any time.
 #include "common.cuh"
+#include "hashgrid_pair.cuh"
 
 namespace {
 
@@ -156,60 +157,6 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
 // tag stage (1 line per cycle per SM) and the L2 atomic units are paced by.  The partial sums of a
 // lane pair are combined with one shuffle.
 constexpr int kPairPoints = kThreads / 2;
-
-// Index arithmetic specialised per level kind (uniform per CTA item, so the branch is free):
-//   HASH : idx = (q0 ^ q1*P1 ^ q2*P2) & (entries-1)      entries a power of two
-//   DENSE: idx = (q0 + q1*res + q2*res^2) & (entries-1)  entries a power of two
-//   ANY  : grid_index() with its general modulo (odd resolutions, non-power-of-two tables)
-// The per-dimension terms are computed once per point; a corner costs one or two XOR/ADDs and an AND.
-enum { kIdxHash = 0, kIdxDense = 1, kIdxAny = 2 };
-
-template <int D, int MODE>
-struct PairTerms {
-  uint32_t t[D][2];     // t[d][bit]: contribution of corner bit `bit` of dimension d (d >= 1)
-  uint32_t q0, mask, entries, res, hashed, swz;
-  uint32_t cell[D];
-  __device__ __forceinline__ void init(const uint32_t (&c)[D], int half, uint32_t entries_, uint32_t res_,
-                                       uint32_t hashed_, uint32_t swz_) {
-    entries = entries_; res = res_; hashed = hashed_; mask = entries_ - 1u; swz = swz_;
-    q0 = c[0] + (uint32_t)half;
-    uint32_t mul = 1u;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      cell[d] = c[d];
-      if (MODE == kIdxHash) mul = (d == 0) ? 1u : (d == 1 ? 2654435761u : 805459861u);
-      t[d][0] = c[d] * mul;
-      t[d][1] = (c[d] + 1u) * mul;
-      if (MODE == kIdxDense) mul *= res_;
-    }
-  }
-  // corner bits of dimensions 1.. in `c` (bit d-1 = dimension d); dimension 0 is this lane's half
-  __device__ __forceinline__ uint32_t index(int c) const {
-    if (MODE == kIdxAny) {
-      uint32_t q[D];
-      q[0] = q0;
-#pragma unroll
-      for (int d = 1; d < D; ++d) q[d] = cell[d] + (uint32_t)((c >> (d - 1)) & 1);
-      return grid_index<D>(q, hashed, entries, res, swz);
-    }
-    uint32_t idx = q0;      // prime 1 / stride 1
-#pragma unroll
-    for (int d = 1; d < D; ++d) {
-      const uint32_t term = t[d][(c >> (d - 1)) & 1];
-      idx = (MODE == kIdxHash) ? (idx ^ term) : (idx + term);
-    }
-    idx &= mask;
-    return (MODE == kIdxHash) ? grid_swizzle(idx, swz) : idx;
-  }
-};
-
-template <int D>
-__device__ __forceinline__ float pair_weight(const float (&frac)[D], float w0, int c) {
-  float w = w0;
-#pragma unroll
-  for (int d = 1; d < D; ++d) w = w * (((c >> (d - 1)) & 1) ? frac[d] : 1.0f - frac[d]);   // (w0 * w1) * w2
-  return w;
-}
 
 // IMMOCO_HG_FWD_PTS points per lane pair and item (the gathers of all of them are issued before the first
 // use: 4 x PTS rows in flight per thread)
@@ -469,6 +416,27 @@ extern "C" int immoco_hashgrid_bwd(const immoco_grid_desc* grid, const float* co
                                    const float* d_enc, float* grad_table, int64_t n_points,
                                    void* stream) {
   return run_bwd(grid, coords, d_enc, grad_table, n_points, 0, grid ? grid->n_levels : 0, stream);
+}
+
+// the levels immoco_mlp_bwd_scatter leaves to the feature planes: every level that is not a power-of-two hashed
+// level (dense levels: run-aggregating kernel)
+extern "C" int immoco_hashgrid_bwd_dense_levels(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
+                                                float* grad_table, int64_t n_points, void* stream) {
+  if (int e = check(grid, n_points)) return e;
+  for (int a = 0; a < grid->n_levels;) {
+    const uint32_t ent = grid->entries[a];
+    const bool fused = grid->hashed[a] != 0u && (ent & (ent - 1u)) == 0u;
+    if (fused) { ++a; continue; }
+    int b = a + 1;
+    while (b < grid->n_levels) {
+      const uint32_t eb = grid->entries[b];
+      if (grid->hashed[b] != 0u && (eb & (eb - 1u)) == 0u) break;
+      ++b;
+    }
+    if (int e = run_bwd(grid, coords, d_enc, grad_table, n_points, a, b, stream)) return e;
+    a = b;
+  }
+  return 0;
 }
 
 // level-range variants (profiling / per-level checks): levels [level_begin, level_end)

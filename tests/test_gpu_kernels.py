@@ -534,3 +534,50 @@ def test_fit_in_stride_wrap_mode_matches_oracle():
         orc.ENCODING_CONFIG.update(saved)
     rel = np.abs(trace - np.asarray(trace_o)) / np.abs(trace_o)
     assert rel[0] < 1e-5 and rel.max() < 1e-3, rel
+
+
+@pytest.mark.parametrize("shape", [(4, 96, 80), (2, 48, 40), (1, 33, 17)])
+@pytest.mark.parametrize("swizzled", [False, True])
+def test_mlp_backward_with_fused_scatter_equals_separate_kernels(native_lib, shape, swizzled):
+    """immoco_mlp_bwd_scatter + immoco_hashgrid_bwd_dense_levels == immoco_mlp_bwd + immoco_hashgrid_bwd: table
+    gradients to the rounding of float atomics, dense-level feature planes bit for bit, weight gradients to rounding."""
+    gs = grid_spec(3, mb.encoding_config)
+    coords = mb.make_grids(shape, "cuda").contiguous()
+    n = coords.shape[0]
+    swz = gs.row_swizzle(np.linspace(-1, 1, shape[0], dtype=np.float32)) if swizzled else ()
+    d = gs.desc(swz)
+    g = torch.Generator(device=DEV).manual_seed(n)
+    enc = torch.randn(16, n, 2, device=DEV, generator=g) * 0.3
+    w = torch.randn(64 * 32 + 16 * 64, device=DEV, generator=g) * 0.2
+    w1, w2 = w[: 64 * 32], w[64 * 32:]
+    d_out = torch.randn(n, 2, device=DEV, generator=g)
+    d_out[::5] = 0.0                                   # zero cotangents are skipped by both paths
+    a = nat.ACT_TANH
+    # separate kernels
+    d_enc_a = torch.empty_like(enc)
+    gw_a = torch.zeros_like(w)
+    gt_a = torch.zeros(gs.n_rows, 2, device=DEV)
+    nat.check(native_lib.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc_a.data_ptr(),
+                                        gw_a.data_ptr(), gw_a.data_ptr() + 4 * 64 * 32, n, 64, a, _s()), "bwd")
+    nat.check(native_lib.immoco_hashgrid_bwd(C.byref(d), coords.data_ptr(), d_enc_a.data_ptr(), gt_a.data_ptr(), n, _s()), "hg")
+    # fused
+    d_enc_b = torch.full_like(enc, float("nan"))
+    gw_b = torch.zeros_like(w)
+    gt_b = torch.zeros(gs.n_rows, 2, device=DEV)
+    nat.check(native_lib.immoco_mlp_bwd_scatter(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(),
+                                                d_enc_b.data_ptr(), gw_b.data_ptr(), gw_b.data_ptr() + 4 * 64 * 32, C.byref(d),
+                                                coords.data_ptr(), gt_b.data_ptr(), n, 64, a, _s()), "bwd_scatter")
+    nat.check(native_lib.immoco_hashgrid_bwd_dense_levels(C.byref(d), coords.data_ptr(), d_enc_b.data_ptr(), gt_b.data_ptr(),
+                                                          n, _s()), "hg_dense")
+    dense = [l for l in range(16) if not gs.hashed[l]]
+    hashed = [l for l in range(16) if gs.hashed[l]]
+    assert dense == [0, 1, 2]
+    assert torch.equal(d_enc_b[dense], d_enc_a[dense])
+    assert bool(torch.isnan(d_enc_b[hashed]).all())              # never written: no round trip for those levels
+    assert rel_l2(gt_b, gt_a) < 2e-6
+    touched = gt_a.abs().sum(1) > 0
+    assert bool((gt_b[~touched] == 0).all())
+    assert rel_l2(gw_b, gw_a) < 1e-5
+    assert native_lib.immoco_mlp_bwd_scatter(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc_b.data_ptr(),
+                                             gw_b.data_ptr(), gw_b.data_ptr(), C.byref(d), coords.data_ptr(), gt_b.data_ptr(),
+                                             n, 256, a, _s()) == nat.ERR_UNSUPPORTED

@@ -220,3 +220,78 @@ def test_row_swizzle_is_a_storage_permutation(hostcheck):
             if gs.hashed[level]:
                 # corner c and c ^ 1 differ in the dim-0 bit: same 16-row line after the permutation
                 assert np.array_equal(idx[0::2] >> 4, idx[1::2] >> 4), (m, level)
+
+
+def test_stride_wrap_level_kinds_match_oracle_in_both_modes():
+    """encoding_config["stride_wrap"]: the package's grid_spec and the oracle agree on which levels hash, in the
+    default (SURVEY contract: levels 6-15 / 3-15 hashed) and in the tiny-cuda-nn uint32-stride mode (levels 12-15
+    index densely); the process-wide default switch is honoured and restored."""
+    from miccai24_immoco_b200 import encoding as enc
+    from oracle import immoco_oracle as orc
+    for dims, first_hashed in ((2, 6), (3, 3)):
+        for wrap in (False, True):
+            gs = enc.grid_spec(dims, dict(mb.encoding_config, stride_wrap=wrap))
+            lv = orc.make_grid_levels(dims, dict(orc.ENCODING_CONFIG, stride_wrap=wrap))
+            assert gs.hashed == tuple(int(v) for v in lv.hashed)
+            want = [int(first_hashed <= l < (12 if wrap else 16)) for l in range(16)]
+            assert list(gs.hashed) == want
+            assert gs.offsets == lv.offsets and gs.entries == lv.entries
+    try:
+        enc.set_stride_wrap_default(True)
+        assert enc.grid_spec(3, mb.encoding_config).hashed[12:] == (0, 0, 0, 0)
+        assert enc.grid_spec(3, dict(mb.encoding_config, stride_wrap=False)).hashed[12:] == (1, 1, 1, 1)   # the key wins
+    finally:
+        enc.set_stride_wrap_default(False)
+    assert enc.grid_spec(3, mb.encoding_config).hashed[12:] == (1, 1, 1, 1)
+    # wrapped dense index of the oracle: third coordinate drops out at level 15 (res 2^19)
+    import torch
+    q = [torch.tensor([5, 5]), torch.tensor([7, 7]), torch.tensor([1, 900])]
+    idx = orc.grid_corner_index(q, 1 << 19, 1 << 19, stride_wrap=True)
+    assert int(idx[0]) == int(idx[1]) == 5
+
+
+def test_batched_movement_group_labels_match_per_slice_extraction():
+    """movement_masks_from_kspace labels a whole stack in one pass: (B, W) labels == the per-slice
+    extract_movement_groups of the reference interface, label count == largest label."""
+    import torch
+    from miccai24_immoco_b200.motion_utils import movement_group_labels
+    from oracle import immoco_oracle as orc
+    g = torch.Generator().manual_seed(3)
+    flags = torch.rand(9, 57, generator=g) > 0.6
+    flags[0] = False
+    flags[1] = True
+    labels = movement_group_labels(flags)
+    for b in range(flags.shape[0]):
+        want = orc.extract_movement_groups(flags[b], make_list=True, height=4)
+        assert int(labels[b].max()) == want.shape[0]
+        got = (labels[b].view(1, 1, -1).expand(1, 4, -1) == torch.arange(1, want.shape[0] + 1).view(-1, 1, 1)).long()
+        assert torch.equal(got, want)
+        assert torch.equal(mb.extract_movement_groups(flags[b], make_list=True, height=4), want)
+
+
+def test_bench_arms_share_one_config_and_every_baseline_config_is_selectable():
+    """bench.py: the GPU arm and the --impl reference arm print the SAME config dict for the driver's comparison;
+    every configuration BASELINE.json names has a --config entry whose workload string names its shape and n_M."""
+    import json
+    import bench
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert len(bench.CONFIGS) == len(base["configs"]) == 5
+    assert sorted(c["index"] for c in bench.CONFIGS.values()) == [0, 1, 2, 3, 4]
+    for name, c in bench.CONFIGS.items():
+        a = bench.config_dict(name, c["n_mov"], 1000, 2)
+        b = bench.config_dict(name, c["n_mov"], 1000, 2)
+        assert a == b and f"{c['h']}x{c['w']}" in a["workload"] and a["baseline_config"] == c["index"]
+    assert "n_M=4" in bench.workload_string("c2", 4, 1000) and "n_M=5" in bench.workload_string("c3", 5, 1000)
+    assert bench.CONFIGS["c3"]["slices"] == 16 and bench.CONFIGS["c4"]["slices"] == 64 and bench.CONFIGS["c5"]["slices"] == 256
+    assert bench.METRIC == base["metric"].split(" at ")[0]
+
+
+def test_run_batched_and_deterministic_flags_are_part_of_the_public_surface():
+    import inspect
+    assert "deterministic" in inspect.signature(mb.imcoco_motion_correction).parameters
+    assert {"deterministic", "batch"} <= set(inspect.signature(mb.reconstruct_batch).parameters)
+    assert {"deterministic", "batch"} <= set(inspect.signature(mb.reconstruct_slices).parameters)
+    assert callable(mb.run_batched) and mb.lib().immoco_max_fit_batch() == 8
+    # positional signature of the reference call is untouched (immoco.py:116)
+    names = list(inspect.signature(mb.imcoco_motion_correction).parameters)[:6]
+    assert names == ["kspace_corr", "masks", "iters", "learning_rate", "lambda_ge", "debug"]
