@@ -1,11 +1,12 @@
 """1000-iteration fits of the headline configuration (C2: 320x320, n_M=4) -- ours against the oracle loop
-run on the same GPU -- shared by tests/test_gpu_long.py (asserts) and tools/long_run_stats.py (the table kept
+run on the same GPU -- shared by tests/test_gpu_zz_long_runs.py (asserts) and tools/long_run_stats.py (the table kept
 under profiles/).
 
 The loop is chaotic: a 1-ulp perturbation of the initial parameters changes the trajectory of
 the ORACLE ITSELF by percents after a few dozen iterations.  A 1000-iteration comparison can therefore only be
-statistical: per slice we record the tail loss (median of the last 50 iterations -- the last sample alone
-sits on or off one of Adam's loss spikes), the final PSNR / SSIM against the ground-truth phantom, and
+statistical: per slice we record the tail loss level (10th percentile of the last 200 iterations -- the last
+sample, and even the median of the last 50, may sit inside one of Adam's loss excursions), the final PSNR / SSIM
+against the ground-truth phantom, and
 compare ours - oracle with oracle(perturbed) - oracle over the same slices."""
 import numpy as np
 import torch
@@ -27,8 +28,11 @@ def summarize(trace, image_abs, gt_abs):
     for t in range(100, len(trace)):
         lo, hi = max(0, t - 25), min(len(trace), t + 26)
         spikes += int(trace[t] > 3.0 * np.median(trace[lo:hi]))
-    return {"tail": float(np.median(trace[-50:])), "last": float(trace[-1]), "max_tail": float(trace[-50:].max()),
-            "spikes": spikes,
+    # "tail" = the level the fit has reached: 10th percentile of the last 200 losses.  The median of the last 50
+    # (kept as tail_median50) is NOT robust: Adam's excursions last tens of iterations, and a run that ends inside
+    # one (oracle and ours alike, 10-25 % of the runs) reports a tail 10-100 x above its own level.
+    return {"tail": float(np.percentile(trace[-200:], 10)), "tail_median50": float(np.median(trace[-50:])),
+            "last": float(trace[-1]), "max_tail": float(trace[-50:].max()), "spikes": spikes,
             "psnr": float(met["psnr"]), "ssim": float(met["ssim"])}
 
 
@@ -78,7 +82,8 @@ def compare(seeds, iters=1000, modes=("deterministic", "atomic"), log=print, n_p
             row[mode] = run_ours(seed, iters, mode == "deterministic")
         rows.append(row)
         log("seed %d: " % seed + "; ".join(
-            "%s tail %.5f last %.5f psnr %.3f ssim %.4f spikes %d" % (k, v["tail"], v["last"], v["psnr"], v["ssim"], v["spikes"])
+            "%s tail %.5f (med50 %.5f) last %.5f psnr %.3f ssim %.4f spikes %d" % (k, v["tail"], v["tail_median50"], v["last"],
+                                                                                   v["psnr"], v["ssim"], v["spikes"])
             for k, v in row.items() if k != "seed"))
     return rows
 

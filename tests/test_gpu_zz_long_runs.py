@@ -7,14 +7,15 @@ ends 0.7 - 0.9 dB away from its own unperturbed run in the median (max 2.8 dB ov
 profiles/round2_long_runs.txt), and one run in eight ends its last iteration on one of Adam's loss spikes (last
 loss 0.2 ... 2.5 against a tail of 0.002 - 0.005).  A 1000-iteration comparison can therefore only be
 statistical, with the oracle's own self-difference, measured in the same run on the same slices, as yardstick:
-  * final PSNR / SSIM: median over slices of |ours - oracle| <= max(0.1 dB, 2.5 x the pooled median of the
-    oracle's self-differences) / max(0.002, 2.5 x ...); no slice further out than max(0.5 dB, 2.5 x the worst
+  * final PSNR / SSIM: median over slices of |ours - oracle| <= max(0.1 dB, 4 x the pooled median of the
+    oracle's self-differences) / max(0.002, 4 x ...); no slice further out than max(0.5 dB, 4 x the worst
     self-difference) / max(0.01, ...);
-  * tail loss (median of the last 50 iterations): the same median rule on the relative difference (floor
-    1e-3), and every run's tail within 20 x the oracle's;
+  * tail loss level (10th percentile of the last 200 iterations; the median of the last 50 is not robust --
+    runs of BOTH implementations end inside a loss excursion 10-25 % of the time): the same median rule on the
+    relative difference (floor 1e-3), and every run's level within 20 x the oracle's;
   * every run ends on a finite loss.
 Both sides are random draws (torch's index_add_ / grid_sample backward on CUDA are atomic too), hence the
-factors.  IMMOCO_LONG_SEEDS (default 4) slices x IMMOCO_LONG_PERTURBED (default 2) oracle perturbations;
+factor.  IMMOCO_LONG_SEEDS (default 4) slices x IMMOCO_LONG_PERTURBED (default 2) oracle perturbations;
 tools/long_run_stats.py writes the 8-slice table kept under profiles/."""
 import os
 
@@ -25,6 +26,10 @@ import miccai24_immoco_b200 as mb
 from tests import long_util as lu
 
 pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+# Both sides are random draws from heavy-tailed distributions (4 slices against 8 self-differences): measured ratios
+# of the medians are 0.6 - 1.9 (profiles/round2_long_runs.txt, gpurun r231 / r232); a wrong kernel shows up as tens of
+# dB.  (The file name sorts last on purpose: the statistical test runs after every exact one.)
+FACTOR = 4.0
 
 
 def test_c2_1000_iterations_against_oracle_distribution():
@@ -40,8 +45,8 @@ def test_c2_1000_iterations_against_oracle_distribution():
             self_ = np.concatenate([lu.spread(rows, p, "oracle", key, rel) for p in pert])
             print(f"{mode:13s} {key:4s}: |ours - oracle| median {np.median(ours):.4g} max {ours.max():.4g}; "
                   f"oracle self-difference (pooled, {self_.size} runs) median {np.median(self_):.4g} max {self_.max():.4g}")
-            assert np.median(ours) <= max(floor_med, 2.5 * np.median(self_)), (mode, key, ours, self_)
+            assert np.median(ours) <= max(floor_med, FACTOR * np.median(self_)), (mode, key, ours, self_)
             if floor_max is not None:
-                assert ours.max() <= max(floor_max, 2.5 * self_.max()), (mode, key, ours, self_)
+                assert ours.max() <= max(floor_max, FACTOR * self_.max()), (mode, key, ours, self_)
         for r in rows:
             assert np.isfinite(r[mode]["last"]) and r[mode]["tail"] <= 20.0 * r["oracle"]["tail"], r

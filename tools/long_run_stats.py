@@ -24,12 +24,14 @@ if __name__ == "__main__":
     print(f"[{time.time() - t0:.0f} s]")
     names = ["deterministic", "atomic", "oracle_perturbed"] + [f"oracle_perturbed{j + 1}" for j in range(1, a.perturbed)]
     for mode in names:
-        for key, rel in (("psnr", False), ("ssim", False), ("tail", True), ("last", True)):
+        for key, rel in (("psnr", False), ("ssim", False), ("tail", True), ("tail_median50", True), ("last", True)):
             d = lu.spread(rows, mode, "oracle", key, rel)
-            print(f"{mode:17s} vs oracle, {key:4s}{' (relative)' if rel else ''}: median {np.median(d):.4g}  max {d.max():.4g}")
+            print(f"{mode:17s} vs oracle, {key:13s}{' (relative)' if rel else ''}: median {np.median(d):.4g}  max {d.max():.4g}")
     for name in ["oracle"] + names:
         last = np.asarray([r[name]["last"] for r in rows])
         tail = np.asarray([r[name]["tail"] for r in rows])
-        print(f"{name:17s}: last-iteration loss min {last.min():.5f} max {last.max():.5f}; tail median min {tail.min():.5f} "
-              f"max {tail.max():.5f}; runs whose last sample is > 10 x their tail median: {(last > 10 * tail).sum()} of {len(rows)}; "
-              f"loss spikes after it 200 (> 10 x tail): {[r[name]['spikes'] for r in rows]}")
+        med50 = np.asarray([r[name]["tail_median50"] for r in rows])
+        print(f"{name:17s}: last-iteration loss min {last.min():.5f} max {last.max():.5f}; tail level (p10 of last 200) min "
+              f"{tail.min():.5f} max {tail.max():.5f}; runs ending inside an excursion (median of last 50 > 3 x level): "
+              f"{(med50 > 3 * tail).sum()} of {len(rows)}; last sample > 10 x level: {(last > 10 * tail).sum()} of {len(rows)}; "
+              f"spikes (> 3 x local median) per run: {[r[name]['spikes'] for r in rows]}")
