@@ -484,7 +484,11 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
   const int n_part_m = (det && M > 0) ? immoco_mlp_bwd_tc_grid(MP) : 0;
 
   cudaStream_t ms = (cudaStream_t)stream;
-  AuxStream* aux = (g_overlap && M > 0) ? aux_for(ms) : nullptr;
+  // The reproducible path runs on ONE stream: its two big kernels (row-sorted gather + Adam of the motion and of the
+  // image grid) are both bound by L2 random gathers and a 420 MB tap stream, and co-running them -- or either of them
+  // beside the other branch -- costs more than it hides (C2: 1037 us per iteration on two streams, 732 on one;
+  // profiles/round2_deterministic_mode_cost.txt).
+  AuxStream* aux = (g_overlap && M > 0 && !det) ? aux_for(ms) : nullptr;
   bool forked = false;          // aux currently carries work that `ms` has not joined
   bool zero_pending = false;    // the previous iteration left its gradients for the deferred memset
 

@@ -6,9 +6,14 @@
 //
 //   build : per level  keys = (row << 32 | point * 2^D + corner)  -> radix sort (CUB, set-up only)
 //           -> taps[k] = {point, weight}, row_ptr[row] = lower bound of the row in the sorted keys
-//   gather: thread (narrow levels) or warp (coarse levels: hundreds of taps per row) per table row:
-//           g[row] = sum_k w_k * d_enc[level][point_k] in tap order -> fixed order, no atomics;
-//           rows without taps are skipped (their gradient / moments stay zero for ever).
+//   gather: g[row] = sum_k w_k * d_enc[plane_k] with a FIXED summation tree per row, no atomics; rows without taps
+//           are skipped (their gradient / moments stay zero for ever).  Coarse levels (hundreds of taps per row):
+//           a warp per row, lane-strided.  All other levels: a warp owns 32 consecutive rows and walks THEIR taps
+//           32 at a time -- lane = tap (coalesced record loads, every lane busy whatever the rows' tap counts: a
+//           thread per row idled half the warp, the counts are Poisson, mean 6, warp maximum ~13), a segmented
+//           scan over the lanes sums the taps of each row inside the step, and the row's owner lane (lane = row)
+//           picks its partial sum up by shuffle and accumulates it step after step.
+//   A tap record is 8 bytes: {plane index (level * n + point) | (row & 31) << 27, weight}.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -16,6 +21,8 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr uint32_t kRidShift = 27;                   // tap.x = plane index (27 bits) | row-in-warp (5 bits)
+constexpr uint32_t kPlaneMask = (1u << kRidShift) - 1u;
 
 template <int D>
 __global__ void __launch_bounds__(kThreads)
@@ -44,11 +51,12 @@ csr_emit_keys_kernel(const __grid_constant__ immoco_grid_desc g, const float* __
 // sorted keys of one level -> {point, weight} records (weight = (w0 * w1) * w2, the forward kernels' order)
 template <int D>
 __global__ void __launch_bounds__(kThreads)
-csr_fill_taps_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords, int level,
+csr_fill_taps_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords, int n, int level,
                      const unsigned long long* __restrict__ keys, uint32_t n_taps, uint2* __restrict__ taps) {
   const float scale = g.scale[level];
   for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < n_taps; k += gridDim.x * kThreads) {
     const uint32_t tap = (uint32_t)(keys[k] & 0xffffffffull);
+    const uint32_t row = (uint32_t)(keys[k] >> 32);
     const uint32_t point = tap >> D, c = tap & ((1u << D) - 1u);
     float w = 1.0f;
 #pragma unroll
@@ -59,7 +67,7 @@ csr_fill_taps_kernel(const __grid_constant__ immoco_grid_desc g, const float* __
       const float wd = ((c >> d) & 1u) ? frac : 1.0f - frac;
       w = (d == 0) ? wd : w * wd;
     }
-    taps[k] = make_uint2(point, __float_as_uint(w));
+    taps[k] = make_uint2(((uint32_t)level * (uint32_t)n + point) | ((row & 31u) << kRidShift), __float_as_uint(w));
   }
 }
 
@@ -118,10 +126,19 @@ __device__ __forceinline__ void finish_row(uint32_t row, float gx, float gy, con
   }
 }
 
-// taps per thread and trip of the narrow path: all index records first, then all gathers, then the
-// ordered sum -- 4 independent L2 round trips in flight per thread (8 measured slower: 282 vs 269 us for the
-// 3-D grid at C2; the gather sits at the measured L2 rate for unpaired 8-byte gathers, profiles/round2_l2_peaks.json)
-constexpr int kUnroll = 4;
+// The tap list is read once per pass and is 4 x larger than everything the gathers hit (420 MB against the 52 MB
+// of cotangent planes and the tables).  Streaming it past L2 (evict-first) so that it does not push the planes
+// out was tried and is slower; the default policy stays.
+#ifndef IMMOCO_CSR_STREAM_TAPS
+#define IMMOCO_CSR_STREAM_TAPS 0      // measured: streaming the taps is SLOWER (serial 329 vs 301 us, iteration 1079 vs ~1010 us)
+#endif
+__device__ __forceinline__ uint2 ld_tap(const uint2* p) {
+#if IMMOCO_CSR_STREAM_TAPS
+  return __ldcs(p);
+#else
+  return __ldg(p);
+#endif
+}
 
 template <bool ADAM>
 __global__ void __launch_bounds__(kThreads)
@@ -136,7 +153,6 @@ hashgrid_bwd_gather_kernel(const __grid_constant__ immoco_grid_desc g, const __g
   const uint32_t cta = blockIdx.x - plan.cta_begin[level];
   const uint32_t entries = g.entries[level];
   const uint32_t off = g.offset[level];
-  const float2* __restrict__ go = d_enc + (size_t)level * n;
   if (plan.wide[level]) {
     const uint32_t r = cta * (kThreads / 32) + (threadIdx.x >> 5);
     if (r >= entries) return;
@@ -147,11 +163,11 @@ hashgrid_bwd_gather_kernel(const __grid_constant__ immoco_grid_desc g, const __g
     if (lane == 0) st = load_row_state<ADAM>(off + r, table, m, v);
     float ax = 0.f, ay = 0.f;
     for (uint32_t k = s + lane; k < e; k += 64) {       // lane-strided, two taps in flight per lane
-      const uint2 t0 = __ldg(taps + k);
+      const uint2 t0 = ld_tap(taps + k);
       const bool two = k + 32 < e;
-      const uint2 t1 = two ? __ldg(taps + k + 32) : make_uint2(0u, 0u);
-      const float2 d0 = __ldg(go + t0.x);
-      const float2 d1 = two ? __ldg(go + t1.x) : make_float2(0.f, 0.f);
+      const uint2 t1 = two ? ld_tap(taps + k + 32) : make_uint2(0u, 0u);
+      const float2 d0 = __ldg(d_enc + (t0.x & kPlaneMask));
+      const float2 d1 = two ? __ldg(d_enc + (t1.x & kPlaneMask)) : make_float2(0.f, 0.f);
       ax = fmaf(__uint_as_float(t0.y), d0.x, ax);
       ay = fmaf(__uint_as_float(t0.y), d0.y, ay);
       ax = fmaf(__uint_as_float(t1.y), d1.x, ax);
@@ -164,26 +180,54 @@ hashgrid_bwd_gather_kernel(const __grid_constant__ immoco_grid_desc g, const __g
     }
     if (lane == 0) finish_row<ADAM>(off + r, ax, ay, st, grad, table, m, v, a);
   } else {
+    // ---- balanced path: this warp owns rows [r0, r0 + 32) of the level; lane = row (owner role) AND lane = tap
+    //      position inside a 32-tap step (worker role)
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t r = cta * kThreads + threadIdx.x;
-    if (r >= entries) return;
-    const uint32_t s = __ldg(row_ptr + off + r), e = __ldg(row_ptr + off + r + 1);
-    if (s == e) return;
-    const RowState st = load_row_state<ADAM>(off + r, table, m, v);
+    const bool row_ok = r < entries;
+    const unsigned rows_mask = __ballot_sync(0xffffffffu, row_ok);
+    if (rows_mask == 0u) return;
+    uint32_t s = 0u, e = 0u;
+    if (row_ok) { s = __ldg(row_ptr + off + r); e = __ldg(row_ptr + off + r + 1); }
+    const uint32_t S = __shfl_sync(0xffffffffu, s, 0);
+    const uint32_t E = __shfl_sync(0xffffffffu, e, 31 - __clz(rows_mask));
+    if (S == E) return;                                   // none of the 32 rows is touched
+    RowState st;
+    if (row_ok && s != e) st = load_row_state<ADAM>(off + r, table, m, v);
     float ax = 0.f, ay = 0.f;
-    for (uint32_t k = s; k < e; k += kUnroll) {
-      uint2 t[kUnroll];
-      float2 d[kUnroll];
+    // one 32-tap step: worker lanes hold contribution c of tap K0 + lane; segmented inclusive scan over the lanes
+    // (taps are sorted by row, so a row's taps are a run of lanes); the owner of a row reads the scan value at the
+    // last lane of its run inside this step
+    auto step = [&](uint32_t K0, uint2 t, float2 d) {
+      const bool valid = K0 + lane < E;
+      const float w = valid ? __uint_as_float(t.y) : 0.f;
+      const uint32_t rid = valid ? (t.x >> kRidShift) : 32u;
+      float cx = w * d.x, cy = w * d.y;
+      const uint32_t rid_prev = __shfl_up_sync(0xffffffffu, rid, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0u || rid_prev != rid);
+      const int run_start = 31 - __clz(heads & (0xffffffffu >> (31u - lane)));
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) t[u] = (k + u < e) ? __ldg(taps + k + u) : make_uint2(0u, 0u);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) d[u] = (k + u < e) ? __ldg(go + t[u].x) : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {                // weight 0 for the padding taps: adds +0
-        ax = fmaf(__uint_as_float(t[u].y), d[u].x, ax);
-        ay = fmaf(__uint_as_float(t[u].y), d[u].y, ay);
+      for (int o = 1; o < 32; o <<= 1) {
+        const float vx = __shfl_up_sync(0xffffffffu, cx, o);
+        const float vy = __shfl_up_sync(0xffffffffu, cy, o);
+        if ((int)lane - o >= run_start) { cx += vx; cy += vy; }
       }
+      const bool has = row_ok && s < K0 + 32u && e > K0 && s != e;
+      const uint32_t last = (e < K0 + 32u ? e : K0 + 32u) - 1u - K0;
+      const float px = __shfl_sync(0xffffffffu, cx, has ? last : 0u);
+      const float py = __shfl_sync(0xffffffffu, cy, has ? last : 0u);
+      if (has) { ax += px; ay += py; }
+    };
+    for (uint32_t K0 = S; K0 < E; K0 += 64u) {            // two steps per trip: both gathers in flight
+      const uint32_t ka = K0 + lane, kb = K0 + 32u + lane;
+      const uint2 ta = ka < E ? ld_tap(taps + ka) : make_uint2(0u, 0u);
+      const uint2 tb = kb < E ? ld_tap(taps + kb) : make_uint2(0u, 0u);
+      const float2 da = ka < E ? __ldg(d_enc + (ta.x & kPlaneMask)) : make_float2(0.f, 0.f);
+      const float2 db = kb < E ? __ldg(d_enc + (tb.x & kPlaneMask)) : make_float2(0.f, 0.f);
+      step(K0, ta, da);
+      if (K0 + 32u < E) step(K0 + 32u, tb, db);           // warp-uniform
     }
-    finish_row<ADAM>(off + r, ax, ay, st, grad, table, m, v, a);
+    if (row_ok && s != e) finish_row<ADAM>(off + r, ax, ay, st, grad, table, m, v, a);
   }
 }
 
@@ -193,6 +237,8 @@ int check(const immoco_grid_desc* g, int64_t n) {
   if (g->n_dims != 2 && g->n_dims != 3) return IMMOCO_ERR_UNSUPPORTED;
   // tap ids (point * 2^D + corner) and tap offsets (level * n * 2^D + k) are 32-bit
   if ((n << g->n_dims) * (int64_t)g->n_levels >= ((int64_t)1 << 32)) return IMMOCO_ERR_UNSUPPORTED;
+  // plane indices (level * n + point) share a word with 5 row-in-warp bits
+  if (n * (int64_t)g->n_levels >= ((int64_t)1 << 27)) return IMMOCO_ERR_UNSUPPORTED;
   return 0;
 }
 
@@ -281,8 +327,8 @@ extern "C" int immoco_hashgrid_csr_build(const immoco_grid_desc* grid, const flo
                                                          32 + row_bits(grid->entries[l]), s);
     if (e != cudaSuccess) return (int)e;
     uint2* out = (uint2*)taps + (size_t)l * n_level;
-    if (D == 2) csr_fill_taps_kernel<2><<<blocks_taps, kThreads, 0, s>>>(*grid, coords, l, keys_b, (uint32_t)n_level, out);
-    else csr_fill_taps_kernel<3><<<blocks_taps, kThreads, 0, s>>>(*grid, coords, l, keys_b, (uint32_t)n_level, out);
+    if (D == 2) csr_fill_taps_kernel<2><<<blocks_taps, kThreads, 0, s>>>(*grid, coords, n, l, keys_b, (uint32_t)n_level, out);
+    else csr_fill_taps_kernel<3><<<blocks_taps, kThreads, 0, s>>>(*grid, coords, n, l, keys_b, (uint32_t)n_level, out);
     IMMOCO_LAUNCH_CHECK();
     const uint32_t entries = grid->entries[l];
     const int last = (l == grid->n_levels - 1) ? 1 : 0;

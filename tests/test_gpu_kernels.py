@@ -330,7 +330,9 @@ def test_hashgrid_csr_structure_and_gather_backward(native_lib, dims, kind):
         idx, w = orc.all_taps(x.cpu(), lv)                       # (L, C, N)
         idx, w = idx.numpy(), w.numpy()
         rows = np.repeat(np.arange(gs.n_rows), np.diff(row_ptr))
-        pts = taps[:, 0].astype(np.int64)
+        word = taps[:, 0].astype(np.int64) & 0xFFFFFFFF
+        pts = word & 0x7FFFFFF                     # plane index = level * n + point ...
+        rid = word >> 27                           # ... | (row within its level & 31) << 27
         wts = taps[:, 1].view(np.float32)
         for level in range(16):
             sl = slice(level * n * c, (level + 1) * n * c)
@@ -340,7 +342,8 @@ def test_hashgrid_csr_structure_and_gather_backward(native_lib, dims, kind):
             o_w = w[level].T.reshape(-1)
             order = np.lexsort((np.arange(n * c), o_rows))
             assert np.array_equal(rows[sl], o_rows[order])
-            assert np.array_equal(pts[sl], o_pts[order])
+            assert np.array_equal(pts[sl], level * n + o_pts[order])
+            assert np.array_equal(rid[sl], (o_rows[order] - gs.offsets[level]) & 31)
             assert np.allclose(wts[sl], o_w[order], rtol=0, atol=1e-7)
     # gather backward vs autograd of the oracle
     g = torch.Generator().manual_seed(3)
@@ -379,8 +382,9 @@ def test_hashgrid_csr_honours_row_swizzle(native_lib):
         grad = torch.zeros(gs.n_rows, 2, device="cuda")
         nat.check(native_lib.immoco_hashgrid_bwd_csr(C.byref(desc), C.byref(cs), d_enc.data_ptr(), grad.data_ptr(), _s()), "csr")
         out[name] = grad
-    # same taps per logical row in the same order -> bit-identical after un-permuting
-    assert torch.equal(out["swz"][perm], out["ref"])
+    # same taps per logical row; the summation tree depends on the neighbouring rows of the physical layout (a warp
+    # walks the taps of its 32 rows in steps of 32), so the two layouts agree to rounding, not bit for bit
+    assert rel_l2(out["swz"][perm], out["ref"]) < 1e-6
 
 
 def test_hashgrid_csr_fused_adam_equals_gather_then_adam(native_lib):

@@ -26,7 +26,9 @@ def timing(h, w, n_mov, iters):
     lam = mb.lambda_schedule(max(iters, 10), 1e-2)[:iters]
     k = case["kspace_motion"]
     k_in = (k / k.abs().max() * 16000).to(DEV)
-    for name, det, fuse in (("atomic", False, False), ("det gather->adam", True, False), ("det fused", True, True)):
+    for name, det, fuse in (("atomic", False, False), ("det gather->adam", True, False), ("det fused", True, True),
+                            ("det fused, one stream", True, True)):
+        lib.immoco_set_branch_overlap(0 if "one stream" in name else 1)
         model = mb.IMMoCo(case["masks"].to(DEV))
         eng = mb.FitEngine(model, iters, deterministic=det, fuse_adam=fuse)
         eng.set_kspace(k_in)
@@ -53,6 +55,7 @@ def timing(h, w, n_mov, iters):
         print(f"[{h}x{w} M={n_mov}] {name:18s}: {best:7.1f} us / iteration (two-stream); serial per-kernel us: {per}; "
               f"serial sum {sum(per.values()):.1f}", flush=True)
         del eng, model
+    lib.immoco_set_branch_overlap(1)
 
 
 def golden(tag):
