@@ -96,7 +96,7 @@ def test_one_iteration_gradients_match_autograd(h, w, n_mov):
 
     Bilinear resampling has a DISCONTINUOUS derivative w.r.t. the sample position at cell borders: a
     rounding-level difference in the displacement flips floor(ix) at an isolated pixel and changes that
-    pixel's grid gradient by O(1) (measured: 2 of 409,600 pixels, tools/tc_diag2.py).  The chain is
+    pixel's grid gradient by O(1) (measured in round 1: 2 of 409,600 pixels; the count is printed below).  The chain is
     therefore checked in two well-conditioned halves around the displacement cotangent."""
     from miccai24_immoco_b200.immoco import _ForwardModelFunction
     case, masks, ours, theirs, _, _ = _models(h, w, n_mov, 7)

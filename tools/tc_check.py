@@ -7,22 +7,42 @@ from miccai24_immoco_b200 import _native as nat
 
 torch.backends.cuda.matmul.allow_tf32 = False
 lib = mb.lib()
+
+
+class _Simt:
+    """the fp32 SIMT check kernels now live in the test-side library tests/checkers/_mlp_simt.so"""
+
+    def __init__(self):
+        import __graft_entry__ as entry
+        h = C.CDLL(entry.build_checkers())
+        P = C.c_void_p
+        h.immoco_simt_mlp_fwd.restype = h.immoco_simt_mlp_bwd.restype = C.c_int
+        h.immoco_simt_mlp_fwd.argtypes = [P, P, P, P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, P]
+        h.immoco_simt_mlp_bwd.argtypes = [P, P, P, P, P, P, P, C.c_int64, C.c_int32, C.c_int32, P]
+        self.immoco_mlp_fwd, self.immoco_mlp_bwd = h.immoco_simt_mlp_fwd, h.immoco_simt_mlp_bwd
+
+
+_simt = _Simt()
+
+
+def impl_lib(impl):
+    return lib if impl == 1 else _simt
+
+
 s = lambda: torch.cuda.current_stream().cuda_stream
 def rel(a, b): return float((a.double() - b.double()).norm() / b.double().norm())
 
 def run_fwd(enc, w1, w2, width, code, out_tanh, impl):
-    lib.immoco_set_mlp_impl(impl)
     n = enc.shape[1]
     out = torch.full((n, 2), float("nan"), device="cuda")
-    nat.check(lib.immoco_mlp_fwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), n, width, code, out_tanh, s()), "fwd")
+    nat.check(impl_lib(impl).immoco_mlp_fwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), n, width, code, out_tanh, s()), "fwd")
     torch.cuda.synchronize()
     return out
 
 def run_bwd(enc, w1, w2, d_out, width, code, impl):
-    lib.immoco_set_mlp_impl(impl)
     n = enc.shape[1]
     d_enc = torch.full_like(enc, float("nan")); g1 = torch.zeros_like(w1); g2 = torch.zeros_like(w2)
-    nat.check(lib.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc.data_ptr(),
+    nat.check(impl_lib(impl).immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc.data_ptr(),
                                  g1.data_ptr(), g2.data_ptr(), n, width, code, s()), "bwd")
     torch.cuda.synchronize()
     return d_enc, g1, g2
@@ -64,21 +84,19 @@ for width, act, n in ((256, nat.ACT_RELU, 102400), (64, nat.ACT_TANH, 409600)):
     for impl in (0, 1):
         for _ in range(3): run_fwd(enc, w1, w2, width, act, 1, impl)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        lib.immoco_set_mlp_impl(impl); out = torch.empty((n, 2), device="cuda")
+        cur = impl_lib(impl); out = torch.empty((n, 2), device="cuda")
         e0.record()
         for _ in range(20):
-            lib.immoco_mlp_fwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), n, width, act, 1, s())
+            cur.immoco_mlp_fwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), n, width, act, 1, s())
         e1.record(); torch.cuda.synchronize()
         msg = f"time fwd W={width} n={n} impl={impl}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us"
         if do_bwd:
             d_enc = torch.empty_like(enc); g1 = torch.zeros_like(w1); g2 = torch.zeros_like(w2)
             for _ in range(3): run_bwd(enc, w1, w2, d_out, width, act, impl)
-            lib.immoco_set_mlp_impl(impl)
             e0.record()
             for _ in range(20):
-                lib.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc.data_ptr(), g1.data_ptr(), g2.data_ptr(), n, width, act, s())
+                cur.immoco_mlp_bwd(enc.data_ptr(), w1.data_ptr(), w2.data_ptr(), d_out.data_ptr(), d_enc.data_ptr(), g1.data_ptr(), g2.data_ptr(), n, width, act, s())
             e1.record(); torch.cuda.synchronize()
             msg += f" | bwd {e0.elapsed_time(e1) / 20 * 1e3:.1f} us"
         print(msg, flush=True)
-lib.immoco_set_mlp_impl(1)
 print("ALL OK" if ok else "FAILURES")
