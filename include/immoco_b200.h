@@ -307,6 +307,16 @@ int immoco_metrics2d(const float* pred, int64_t pred_img_stride, int64_t pred_ro
                      int32_t gt_complex, int32_t batch, int32_t h, int32_t w, int32_t kernel_size,
                      int32_t pool, float* minmax, double* acc, void* stream);
 
+/* HaarPSI of the same min-max-normalised image pairs (piq.haarpsi(data_range=1, scales=3), evaluate.py:76):
+ * minmax = what immoco_metrics2d wrote for these views; pooled = scratch of batch*2*hp*wp floats with
+ * hp = (h + d) / 2, wp = (w + d) / 2, d = max(h % 2, w % 2); acc (batch*2 doubles, ZEROED by the caller) receives
+ * {sum of sigmoid(alpha * similarity) * weight, sum of weight}; the score is (logit((acc0 + eps) / (acc1 + eps)) /
+ * alpha)^2 with eps = FLT_EPSILON.  piq is not available here: parity unpinned (restated algorithm). */
+int immoco_haarpsi(const float* pred, int64_t pred_img_stride, int64_t pred_row_stride, int32_t pred_complex,
+                   const float* gt, int64_t gt_img_stride, int64_t gt_row_stride, int32_t gt_complex,
+                   int32_t batch, int32_t h, int32_t w, float c, float alpha, const float* minmax, float* pooled,
+                   double* acc, void* stream);
+
 /* ---- (10) synthetic rigid motion: the image-domain half of motion_simulation2D
  *          (src/utils/motion_utils.py:121-202).  theta: (n_mov, 6) affine rows as handed to
  *          F.affine_grid(align_corners=True); out: (n_mov, h, w) complex, bilinear, border padding,

@@ -136,6 +136,8 @@ _SIGNATURES = {
     "immoco_max_fit_batch": (C.c_int, []),
     "immoco_metrics2d": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "immoco_haarpsi": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P]),
     "immoco_rigid_resample": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_replace_lines": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "immoco_unet_conv3x3": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,

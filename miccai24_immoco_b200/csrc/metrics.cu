@@ -164,7 +164,116 @@ ssim_mse_kernel(View pred, View gt, const float* __restrict__ mm, double* __rest
   }
 }
 
+// ---- HaarPSI (piq.haarpsi as called at src/utils/evaluate.py:76; restated in oracle/immoco_oracle.py:haarpsi01) ----
+// pooled[b][which][i][j] = 2x2 average of 255 * min-max-normalised pixel (zero beyond the image: odd sizes are padded)
+__global__ void __launch_bounds__(kThreads)
+haar_pool_kernel(View pred, View gt, const float* __restrict__ mm, float* __restrict__ pooled, int h, int w, int hp,
+                 int wp) {
+  const int b = blockIdx.z, which = blockIdx.y;
+  const View& v = which ? gt : pred;
+  const float lo = mm[4 * b + 2 * which], inv = 255.0f / ((mm[4 * b + 2 * which + 1] - lo) + 1e-24f);
+  float* out = pooled + ((size_t)(b * 2 + which) * hp) * wp;
+  for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < hp * wp; idx += gridDim.x * kThreads) {
+    const int i = idx / wp, j = idx - i * wp;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int y = 2 * i + (t >> 1), x = 2 * j + (t & 1);
+      if (y < h && x < w) s += (load_px(v, b, y, x) - lo) * inv;
+    }
+    out[idx] = 0.25f * s;
+  }
+}
+
+// Haar responses at kernel sizes 2 / 4 / 8 in two orientations ('same' zero padding: k/2 - 1 before, k/2 after),
+// local similarity of the two finest scales, weight = larger magnitude at the coarsest; acc[b] += {sum sigmoid(alpha S) W, sum W}
+__device__ __forceinline__ void haar_coeffs(const float* __restrict__ img, int hp, int wp, int i, int j, float (&co)[6]) {
+#pragma unroll
+  for (int sc = 0; sc < 3; ++sc) {
+    const int k = 2 << sc, off = k / 2 - 1;
+    float hsum = 0.f, vsum = 0.f;
+    for (int a = 0; a < k; ++a) {
+      const int y = i + a - off;
+      if (y < 0 || y >= hp) continue;
+      for (int c = 0; c < k; ++c) {
+        const int x = j + c - off;
+        if (x < 0 || x >= wp) continue;
+        const float v = __ldg(img + (size_t)y * wp + x);
+        hsum += (a < k / 2) ? v : -v;          // haar_filter: second half of the ROWS negative
+        vsum += (c < k / 2) ? v : -v;          // its transpose: second half of the COLUMNS negative
+      }
+    }
+    co[2 * sc] = hsum / (float)k;
+    co[2 * sc + 1] = vsum / (float)k;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+haar_sim_kernel(const float* __restrict__ pooled, double* __restrict__ acc, int hp, int wp, float cst, float alpha) {
+  const int b = blockIdx.z;
+  const float* px = pooled + ((size_t)(b * 2) * hp) * wp;
+  const float* py = px + (size_t)hp * wp;
+  double num = 0.0, den = 0.0;
+  for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < hp * wp; idx += gridDim.x * kThreads) {
+    const int i = idx / wp, j = idx - i * wp;
+    float cx[6], cy[6];
+    haar_coeffs(px, hp, wp, i, j, cx);
+    haar_coeffs(py, hp, wp, i, j, cy);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float sim = 0.f;
+#pragma unroll
+      for (int sc = 0; sc < 2; ++sc) {
+        const float a = fabsf(cx[2 * sc + o]), bb = fabsf(cy[2 * sc + o]);
+        sim += (2.f * a * bb + cst) / (a * a + bb * bb + cst);
+      }
+      sim *= 0.5f;
+      const float wgt = fmaxf(fabsf(cx[4 + o]), fabsf(cy[4 + o]));
+      num += (double)(wgt / (1.f + expf(-alpha * sim)));
+      den += (double)wgt;
+    }
+  }
+  __shared__ double red[2][kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = num; red[1][threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, d = 0.0;
+    for (int wv = 0; wv < kThreads / 32; ++wv) { a += red[0][wv]; d += red[1][wv]; }
+    atomicAdd(acc + 2 * b, a);
+    atomicAdd(acc + 2 * b + 1, d);
+  }
+}
+
 }  // namespace
+
+// minmax: the (batch, 4) floats immoco_metrics2d produced for the same views.  pooled: scratch of
+// batch * 2 * hp * wp floats (hp, wp = the 2x2-pooled size of the zero-padded image).  acc: batch * 2 doubles, ZEROED.
+extern "C" int immoco_haarpsi(const float* pred, int64_t pred_img_stride, int64_t pred_row_stride, int32_t pred_complex,
+                              const float* gt, int64_t gt_img_stride, int64_t gt_row_stride, int32_t gt_complex,
+                              int32_t batch, int32_t h, int32_t w, float c, float alpha, const float* minmax,
+                              float* pooled, double* acc, void* stream) {
+  if (!pred || !gt || !minmax || !pooled || !acc || batch < 0 || h < 1 || w < 1) return IMMOCO_ERR_BAD_ARG;
+  if (batch == 0) return 0;
+  if (batch > 65535) return IMMOCO_ERR_UNSUPPORTED;
+  const int dp = (h % 2) > (w % 2) ? (h % 2) : (w % 2);
+  const int hp = (h + dp) / 2, wp = (w + dp) / 2;
+  if (h < 16 || w < 16) return IMMOCO_ERR_UNSUPPORTED;        // piq: the image must hold the 2^(scales+1) kernel
+  cudaStream_t s = (cudaStream_t)stream;
+  View vp{pred, pred_img_stride, pred_row_stride, pred_complex};
+  View vg{gt, gt_img_stride, gt_row_stride, gt_complex};
+  int gx = (hp * wp + kThreads - 1) / kThreads;
+  if (gx > 1024) gx = 1024;
+  haar_pool_kernel<<<dim3(gx, 2, batch), kThreads, 0, s>>>(vp, vg, minmax, pooled, h, w, hp, wp);
+  IMMOCO_LAUNCH_CHECK();
+  haar_sim_kernel<<<dim3(gx, 1, batch), kThreads, 0, s>>>(pooled, acc, hp, wp, c, alpha);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
 
 // pred / gt: (batch, h, w) views with element strides (complex views are read as magnitudes).
 // minmax: batch*4 floats scratch; acc: batch*4 doubles, ZEROED by the caller, receives

@@ -5,14 +5,13 @@ Host-side mirror of src/utils/evaluate.py: ``normalize`` (:19-29), ``rmse`` (:32
 ``piq.ssim(kernel_size=11, data_range=1.0)`` (piq 0.8.0, absent here: parity unpinned, restated from
 its published algorithm -- Gaussian sigma 1.5, k1=0.01, k2=0.03, valid convolution, average-pool
 down-sampling by max(1, round(min(H,W)/256))) runs as one CUDA kernel together with the squared error;
-nothing is copied to the host: the four results are 0-dim CUDA tensors.  HaarPSI (piq.haarpsi) is not
-on the acceptance path (BASELINE.json names PSNR / SSIM) and is returned as NaN.
+nothing is copied to the host: the four results are 0-dim CUDA tensors.  HaarPSI (piq.haarpsi(scales=3),
+evaluate.py:76) is two more small kernels on the same normalised pairs -- restated from its published algorithm
+like SSIM (parity unpinned: piq is absent).
 """
 from __future__ import annotations
 
 import numpy as np
-import warnings
-
 import torch
 
 from . import _native as nat
@@ -55,7 +54,7 @@ def _view(t: torch.Tensor):
     return t, t.data_ptr(), t.stride(0), t.stride(2), 1 if t.is_complex() else 0
 
 
-def metric_sums(pred_recon: torch.Tensor, gt_recon: torch.Tensor, kernel_size: int = 11) -> torch.Tensor:
+def metric_sums(pred_recon: torch.Tensor, gt_recon: torch.Tensor, kernel_size: int = 11, haarpsi: bool = False):
     """(B, 4) float64 CUDA tensor: per image {sum of squared error of the min-max-normalised images,
     sum of the SSIM map, SSIM map size, 0}.  Inputs may be crops (strided views) and complex."""
     _need_cuda(pred_recon, "calmetric2D")
@@ -68,12 +67,19 @@ def metric_sums(pred_recon: torch.Tensor, gt_recon: torch.Tensor, kernel_size: i
     pool = max(1, round(min(h, w) / 256))
     minmax = torch.empty((b, 4), dtype=torch.float32, device=p.device)
     acc = torch.zeros((b, 4), dtype=torch.float64, device=p.device)
-    nat.check(nat.lib().immoco_metrics2d(p_ptr, p_is, p_rs, p_c, g_ptr, g_is, g_rs, g_c, b, h, w, kernel_size, pool,
-                                         minmax.data_ptr(), acc.data_ptr(), _stream()), "metrics2d")
-    return acc
-
-
-_HAARPSI_WARNED = False
+    with torch.cuda.device(p.device):
+        s = _stream(p.device)
+        nat.check(nat.lib().immoco_metrics2d(p_ptr, p_is, p_rs, p_c, g_ptr, g_is, g_rs, g_c, b, h, w, kernel_size, pool,
+                                             minmax.data_ptr(), acc.data_ptr(), s), "metrics2d")
+        if haarpsi and h >= 16 and w >= 16:
+            # piq.haarpsi(scales=3) on the same normalised pairs (evaluate.py:76); parity unpinned like SSIM
+            dp = max(h % 2, w % 2)
+            pooled = torch.empty((b, 2, (h + dp) // 2, (w + dp) // 2), dtype=torch.float32, device=p.device)
+            hacc = torch.zeros((b, 2), dtype=torch.float64, device=p.device)
+            nat.check(nat.lib().immoco_haarpsi(p_ptr, p_is, p_rs, p_c, g_ptr, g_is, g_rs, g_c, b, h, w, 30.0, 4.2,
+                                               minmax.data_ptr(), pooled.data_ptr(), hacc.data_ptr(), s), "haarpsi")
+            return acc, hacc
+    return (acc, None) if haarpsi else acc
 
 
 def calmetric2D(pred_recon: torch.Tensor, gt_recon: torch.Tensor):
@@ -85,20 +91,18 @@ def calmetric2D(pred_recon: torch.Tensor, gt_recon: torch.Tensor):
     ssim_kernel = 11
     if w < ssim_kernel or h < ssim_kernel:
         ssim_kernel = min(w, h, ssim_kernel) - 1
-    acc = metric_sums(pred_recon, gt_recon, ssim_kernel)
+    acc, hacc = metric_sums(pred_recon, gt_recon, ssim_kernel, haarpsi=True)
     n_px = float(h * w)
     mse = acc[:, 0] / n_px
     psnr = (20 * torch.log10(1.0 / torch.sqrt(mse))).mean().float()
     ssim = (acc[:, 1] / acc[:, 2]).mean().float()
     rmse_all = torch.sqrt(acc[:, 0].sum() / (n_px * acc.shape[0])).float()
-    # HaarPSI (piq.haarpsi at evaluate.py:72) is NOT implemented on this path: the third return value is NaN.  A
-    # caller that aggregates it like the reference's tables (test_immoco.py:77-85) must drop that column; warn once.
-    global _HAARPSI_WARNED
-    if not _HAARPSI_WARNED:
-        warnings.warn("miccai24_immoco_b200.calmetric2D: HaarPSI is not implemented on the CUDA path; the third "
-                      "returned value is NaN (PSNR, SSIM and RMSE are computed)", RuntimeWarning, stacklevel=2)
-        _HAARPSI_WARNED = True
-    haar = torch.full((), float("nan"), device=acc.device)
+    if hacc is None:          # images smaller than HaarPSI's 16-pixel kernel (piq raises there)
+        haar = torch.full((), float("nan"), device=acc.device)
+    else:
+        eps = float(torch.finfo(torch.float32).eps)
+        score = (hacc[:, 0] + eps) / (hacc[:, 1] + eps)
+        haar = ((torch.log(score / (1.0 - score)) / 4.2) ** 2).mean().float()
     return psnr, ssim, haar, rmse_all
 
 

@@ -685,6 +685,41 @@ def ssim01(pred: torch.Tensor, gt: torch.Tensor, kernel_size: int = 11, sigma: f
     return float(ss.mean())
 
 
+def haarpsi01(pred: torch.Tensor, gt: torch.Tensor, scales: int = 3, c: float = 30.0, alpha: float = 4.2) -> float:
+    """piq.haarpsi(data_range=1, scales=3, subsample=True, c=30, alpha=4.2) on (H,W) images in [0,1] [ext]
+    (called at src/utils/evaluate.py:76).  piq 0.8.0 is absent here -> **parity unpinned**; this restates its
+    published algorithm (Reisenhofer et al. 2018): scale to [0, 255], 2x2 average down-sampling, Haar responses at
+    kernel sizes 2 / 4 / 8 in two orientations with 'same' zero padding (k/2 - 1 before, k/2 after), local
+    similarity (2ab + c) / (a^2 + b^2 + c) averaged over the two finest scales, weighted by the coarsest scale's
+    larger magnitude through a sigmoid, and the final (logit(.) / alpha)^2."""
+    if scales != 3:
+        raise ValueError("only scales=3 is meaningful in piq.haarpsi (its channel indices are hard-wired)")
+    x = pred[None, None].double() * 255.0
+    y = gt[None, None].double() * 255.0
+    down = max(x.shape[2] % 2, x.shape[3] % 2)
+    x, y = F.pad(x, [0, down, 0, down]), F.pad(y, [0, down, 0, down])
+    x, y = F.avg_pool2d(x, 2, 2), F.avg_pool2d(y, 2, 2)
+    cx, cy = [], []
+    for scale in range(scales):
+        k = 2 ** (scale + 1)
+        ker = torch.ones(k, k, dtype=torch.float64) / k
+        ker[k // 2:, :] = -ker[k // 2:, :]
+        kernels = torch.stack([ker, ker.t()])[:, None]                      # (2, 1, k, k)
+        pad = [k // 2 - 1, k // 2, k // 2 - 1, k // 2]
+        cx.append(F.conv2d(F.pad(x, pad), kernels))
+        cy.append(F.conv2d(F.pad(y, pad), kernels))
+    cx, cy = torch.cat(cx, 1), torch.cat(cy, 1)                             # (1, 6, H, W)
+    weights = torch.max(cx[:, 4:].abs(), cy[:, 4:].abs())                   # coarsest scale, both orientations
+    sims = []
+    for o in range(2):
+        a, b = cx[:, (o, o + 2)].abs(), cy[:, (o, o + 2)].abs()
+        sims.append(((2 * a * b + c) / (a * a + b * b + c)).sum(1, keepdim=True) / 2)
+    sim = torch.cat(sims, 1)
+    eps = torch.finfo(torch.float32).eps
+    score = ((torch.sigmoid(sim * alpha) * weights).sum() + eps) / (weights.sum() + eps)
+    return float((torch.log(score / (1 - score)) / alpha) ** 2)
+
+
 def crop_metrics(pred_abs: torch.Tensor, gt_abs: torch.Tensor):
     """Central-half crop + min-max normalise + PSNR/SSIM/RMSE (test_immoco.py:74-85)."""
     h, w = gt_abs.shape
@@ -692,4 +727,4 @@ def crop_metrics(pred_abs: torch.Tensor, gt_abs: torch.Tensor):
     p = normalize01(pred_abs[ch:-ch, cw:-cw].float())
     g = normalize01(gt_abs[ch:-ch, cw:-cw].float())
     return {"psnr": psnr01(p, g), "ssim": ssim01(p, g),
-            "rmse": float(torch.sqrt(torch.mean((p - g) ** 2)))}
+            "rmse": float(torch.sqrt(torch.mean((p - g) ** 2))), "haarpsi": haarpsi01(p, g)}

@@ -81,17 +81,24 @@ def test_calmetric2d_matches_oracle(h, w):
     assert abs(float(psnr) - want_psnr) < 1e-3          # dB
     assert abs(float(ssim) - want_ssim) < 2e-5
     assert abs(float(rmse) - want_rmse) < 1e-6
-    assert np.isnan(float(haar))
+    # HaarPSI (piq.haarpsi restated, like SSIM parity unpinned): odd sizes exercise the zero-padded 2x2 pooling
+    assert abs(float(haar) - orc.haarpsi01(p, g)) < 2e-5
 
 
 def test_calmetric2d_batch_and_helpers():
     pairs = [_pair(96, 80, s) for s in (1, 2, 3)]
     pred = torch.stack([p for p, _ in pairs])[:, None].to(DEV)
     gt = torch.stack([g for _, g in pairs])[:, None].to(DEV)
-    psnr, ssim, _, rmse = mb.calmetric2D(pred, gt)
+    psnr, ssim, haar, rmse = mb.calmetric2D(pred, gt)
     pn, gn = mb.normalize(pred), mb.normalize(gt)               # batch-wise, like evaluate.py:19-29
     ws = [orc.ssim01(pn[i, 0].cpu(), gn[i, 0].cpu()) for i in range(3)]
     assert abs(float(ssim) - float(np.mean(ws))) < 2e-5
+    hs = [orc.haarpsi01(pn[i, 0].cpu(), gn[i, 0].cpu()) for i in range(3)]
+    assert abs(float(haar) - float(np.mean(hs))) < 2e-5
+    same = mb.calmetric2D(gt, gt)
+    assert abs(float(same[2]) - 1.0) < 1e-5 and float(same[1]) > 0.99999          # identical images: HaarPSI = SSIM = 1
+    tiny = mb.calmetric2D(pred[:, :, :12, :12], gt[:, :, :12, :12])                 # below HaarPSI's 16-pixel kernel
+    assert np.isnan(float(tiny[2])) and np.isfinite(float(tiny[0]))
     assert abs(float(psnr) - float(mb.my_psnr(pn, gn, data_range=1.0))) < 1e-3
     assert abs(float(rmse) - float(mb.rmse(pn, gn))) < 1e-6
     with pytest.raises(ValueError):

@@ -106,6 +106,57 @@ def test_metrics_sane():
     a = torch.rand(64, 64)
     m = orc.crop_metrics(a, a)
     assert m["ssim"] > 0.999999 and m["rmse"] == 0.0
+    assert abs(m["haarpsi"] - 1.0) < 1e-6
+
+
+def _haarpsi_loops(x, y, c=30.0, alpha=4.2):
+    """HaarPSI written out pixel by pixel in numpy (an independent statement of the published algorithm that
+    piq.haarpsi implements; piq itself is absent here, the seam stays 'parity unpinned')."""
+    def pool(a):
+        d = max(a.shape[0] % 2, a.shape[1] % 2)
+        a = np.pad(a * 255.0, ((0, d), (0, d)))
+        a = a[:a.shape[0] // 2 * 2, :a.shape[1] // 2 * 2]            # avg_pool2d floors: a last odd row / column drops
+        return 0.25 * (a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])
+
+    def coeff(a, k, transpose):
+        h, w = a.shape
+        out = np.zeros((h, w))
+        off = k // 2 - 1
+        for i in range(h):
+            for j in range(w):
+                s = 0.0
+                for u in range(k):
+                    for v in range(k):
+                        yy, xx = i + u - off, j + v - off
+                        if 0 <= yy < h and 0 <= xx < w:
+                            neg = (v >= k // 2) if transpose else (u >= k // 2)
+                            s += -a[yy, xx] if neg else a[yy, xx]
+                out[i, j] = s / k
+        return out
+
+    px, py = pool(x), pool(y)
+    num = den = 0.0
+    for o in (False, True):
+        cx = [np.abs(coeff(px, k, o)) for k in (2, 4, 8)]
+        cy = [np.abs(coeff(py, k, o)) for k in (2, 4, 8)]
+        sim = sum((2 * a * b + c) / (a * a + b * b + c) for a, b in zip(cx[:2], cy[:2])) / 2
+        wgt = np.maximum(cx[2], cy[2])
+        num += (wgt / (1 + np.exp(-alpha * sim))).sum()
+        den += wgt.sum()
+    eps = float(np.finfo(np.float32).eps)
+    s = (num + eps) / (den + eps)
+    return (np.log(s / (1 - s)) / alpha) ** 2
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (21, 18), (24, 33)])
+def test_haarpsi_oracle_equals_pixel_loops(hw):
+    g = torch.Generator().manual_seed(hw[0] * 100 + hw[1])
+    x = torch.rand(hw, generator=g, dtype=torch.float64)
+    y = (x + 0.2 * torch.rand(hw, generator=g, dtype=torch.float64)).clamp(0, 1)
+    want = _haarpsi_loops(x.numpy(), y.numpy())
+    got = orc.haarpsi01(x, y)
+    assert 0.0 < got < 1.0 and abs(got - want) < 1e-10
+    assert orc.haarpsi01(x, (x + 0.6 * torch.rand(hw, generator=g, dtype=torch.float64)).clamp(0, 1)) < got
 
 
 def test_kld_net_oracle_against_reference_unet_golden(golden_dir):
