@@ -122,6 +122,32 @@ int immoco_hashgrid_bwd_csr_adam(const immoco_grid_desc* grid, const immoco_grid
                                  float* table, float* exp_avg, float* exp_avg_sq, float* grad_table, double lr,
                                  double beta1, double beta2, double eps, int32_t step, void* stream);
 
+/* ---- (1c) tap-indexed storage of the hashed levels.  With constant coordinates the rows a point touches can be
+ *          looked up once (immoco_hashgrid_tap_rows: level-relative physical rows, [level][point][2^n_dims]
+ *          uint32) and the hashed levels stored in ANY row order; the caller ranks the rows by first touch
+ *          (miccai24_immoco_b200/immoco.py:GridTaps), which puts the rows nobody ever touches -- 47 % of the 2-D
+ *          image grid's hashed rows at 320 x 320: g = m = v = 0 for ever under torch.optim.Adam
+ *          (src/models/immoco.py:149-154) -- behind the n_active_rows live ones, where Adam and the gradient
+ *          memset never go, and makes a pixel's first-touched rows consecutive.  `rows` then holds ABSOLUTE
+ *          physical rows (relative to the table base) of the levels >= first_level, 16-byte aligned; levels
+ *          below first_level keep their own index arithmetic.  2-D grids only. ---- */
+typedef struct immoco_grid_taps {
+  const uint32_t* rows;      /* (n_levels - first_level) x n_points x 4 absolute rows; NULL = not used      */
+  int32_t first_level;       /* levels [first_level, n_levels) are tap-indexed                               */
+  int32_t reserved;
+  int64_t n_points;
+  int64_t n_active_rows;     /* rows [0, n_active_rows) of the table hold everything any point touches       */
+} immoco_grid_taps;
+int immoco_hashgrid_tap_rows(const immoco_grid_desc* grid, const float* coords, int64_t n_points,
+                             int32_t level_begin, int32_t level_end, uint32_t* rows, void* stream);
+/* immoco_hashgrid_fwd / immoco_hashgrid_bwd over a table whose levels >= taps->first_level are stored in the
+ * order `taps->rows` describes (forward: one launch, bit-identical features; backward: dense-level launch +
+ * one indexed launch) */
+int immoco_hashgrid_fwd_taps(const immoco_grid_desc* grid, const immoco_grid_taps* taps, const float* coords,
+                             const float* table, float* enc, int64_t n_points, void* stream);
+int immoco_hashgrid_bwd_taps(const immoco_grid_desc* grid, const immoco_grid_taps* taps, const float* coords,
+                             const float* d_enc, float* grad_table, int64_t n_points, void* stream);
+
 /* ---- (2) INR MLP: replaces the network half of tcnn.NetworkWithInputEncoding
  *          (configs at src/models/immoco.py:11-25).  One hidden layer of `width` (64 or 256),
  *          no biases, W1: width x 32, W2: 16 x width (rows >= 2 are padding).
@@ -247,6 +273,10 @@ typedef struct immoco_fit {
   float* mlp_part_motion;          /* immoco_mlp_bwd_partial_count(M*P) x n_mlp_motion floats, zeroed */
   int64_t* d_image_fx;             /* 2*P int64, zeroed by the caller once                    */
   uint32_t* dc_max_bits;           /* one word per iteration, zeroed by the caller            */
+  /* ---- float-atomic path only (ignored when deterministic): taps_image.rows != NULL = the image table's levels
+   * >= first_level are stored tap-indexed (section 1c): the image branch runs immoco_hashgrid_fwd_taps /
+   * _bwd_taps, and Adam + gradient zeroing stop after the MLP block + 2 * n_active_rows floats. */
+  immoco_grid_taps taps_image;
 } immoco_fit;
 /* doubles per iteration of immoco_fit::loss_slots for an (h, w) slice: out[0] column-pass CTAs (data
  * consistency), out[1] gradient-entropy CTAs; slots_per_iter = out[0] + out[1] */
@@ -367,7 +397,7 @@ int immoco_rigid_bicubic_bwd_theta(const float* images, const float* theta, cons
 int immoco_abi_version(void);
 /* sizeof(immoco_grid_desc), sizeof(immoco_lines), sizeof(immoco_fit), sizeof(immoco_grid_csr): lets a
  * foreign-language binding assert that its struct mirrors match this build. */
-void immoco_struct_sizes(int32_t out[4]);
+void immoco_struct_sizes(int32_t out[5]);
 int immoco_launches_per_iteration(int32_t m);
 /* the same for a fit with immoco_fit::deterministic / fuse_adam set */
 int immoco_launches_per_iteration_mode(int32_t m, int32_t deterministic, int32_t fuse_adam);

@@ -48,6 +48,16 @@ class GridCsr(C.Structure):
     ]
 
 
+class GridTaps(C.Structure):
+    _fields_ = [
+        ("rows", C.c_void_p),
+        ("first_level", C.c_int32),
+        ("reserved", C.c_int32),
+        ("n_points", C.c_int64),
+        ("n_active_rows", C.c_int64),
+    ]
+
+
 class Lines(C.Structure):
     _fields_ = [
         ("n_groups", C.c_int32),
@@ -84,6 +94,7 @@ class Fit(C.Structure):
         ("csr_image", GridCsr), ("csr_motion", GridCsr),
         ("mlp_part_image", C.c_void_p), ("mlp_part_motion", C.c_void_p),
         ("d_image_fx", C.c_void_p), ("dc_max_bits", C.c_void_p),
+        ("taps_image", GridTaps),
     ]
 
 
@@ -101,6 +112,9 @@ _SIGNATURES = {
     "immoco_hashgrid_bwd_csr": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P]),
     "immoco_hashgrid_bwd_csr_adam": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P, _P, _P, C.c_double,
                                                C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
+    "immoco_hashgrid_tap_rows": (C.c_int, [C.POINTER(GridDesc), _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    "immoco_hashgrid_fwd_taps": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridTaps), _P, _P, _P, C.c_int64, _P]),
+    "immoco_hashgrid_bwd_taps": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridTaps), _P, _P, _P, C.c_int64, _P]),
     "immoco_mlp_bwd_partials": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "immoco_mlp_bwd_scatter": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(GridDesc), _P, _P, C.c_int64, C.c_int32,
                                          C.c_int32, _P]),
@@ -206,9 +220,9 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)     # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        sizes = (C.c_int32 * 4)()
+        sizes = (C.c_int32 * 5)()
         handle.immoco_struct_sizes(sizes)
-        want = (C.sizeof(GridDesc), C.sizeof(Lines), C.sizeof(Fit), C.sizeof(GridCsr))
+        want = (C.sizeof(GridDesc), C.sizeof(Lines), C.sizeof(Fit), C.sizeof(GridCsr), C.sizeof(GridTaps))
         if tuple(sizes) != want:
             raise RuntimeError(f"struct layout mismatch: library {tuple(sizes)} vs binding {want}")
         _lib = handle

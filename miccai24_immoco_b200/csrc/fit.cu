@@ -244,13 +244,14 @@ extern "C" int immoco_adam_step_partials(float* params, const float* g_part, int
   return 0;
 }
 
-extern "C" int immoco_abi_version(void) { return 2; }
+extern "C" int immoco_abi_version(void) { return 3; }
 
-extern "C" void immoco_struct_sizes(int32_t out[4]) {
+extern "C" void immoco_struct_sizes(int32_t out[5]) {
   out[0] = (int32_t)sizeof(immoco_grid_desc);
   out[1] = (int32_t)sizeof(immoco_lines);
   out[2] = (int32_t)sizeof(immoco_fit);
   out[3] = (int32_t)sizeof(immoco_grid_csr);
+  out[4] = (int32_t)sizeof(immoco_grid_taps);
 }
 
 // launches per iteration.  Float-atomic path: hashgrid fwd + mlp fwd (x2), gradient entropy, fused rows
@@ -464,6 +465,12 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
     if ((f->deterministic != 0) != det || (det && (f->fuse_adam != 0) != fuse_adam)) return IMMOCO_ERR_BAD_ARG;
     if (f->n_motion != f0->n_motion || f->n_image != f0->n_image || (f->n_motion & 3) != 0) return IMMOCO_ERR_BAD_ARG;
     if ((f->loss_slots == nullptr) != (f0->loss_slots == nullptr)) return IMMOCO_ERR_BAD_ARG;
+    // tap-indexed image table: all fits of a batch share the shape, hence the tap list and the live-row count
+    if ((f->taps_image.rows == nullptr) != (f0->taps_image.rows == nullptr)) return IMMOCO_ERR_BAD_ARG;
+    if (!det && f->taps_image.rows &&
+        (f->taps_image.n_points != (int64_t)H * W || f->taps_image.n_active_rows != f0->taps_image.n_active_rows ||
+         f->taps_image.n_active_rows < 0 || f->taps_image.n_active_rows > (int64_t)f->grid_image.offset[f->grid_image.n_levels]))
+      return IMMOCO_ERR_BAD_ARG;
     if (det) {
       if (!f->loss_slots || !f->d_image_fx || !f->dc_max_bits || !f->mlp_part_image || !f->csr_image.row_ptr ||
           !f->csr_image.taps)
@@ -477,6 +484,14 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
   const int64_t mlp_m = (int64_t)wm * 32 + 16 * (int64_t)wm;
   const int64_t mlp_i = (int64_t)wi * 32 + 16 * (int64_t)wi;
   const int64_t n_mot = f0->n_motion;
+  // floats of the image INR that Adam and the gradient memset visit: everything, or (tap-indexed table) the MLP
+  // block + the rows some pixel touches, rounded up to a 128-bit item
+  const bool taps_i = !det && f0->taps_image.rows != nullptr;
+  int64_t n_img_live = f0->n_image;
+  if (taps_i) {
+    n_img_live = (mlp_i + 2 * f0->taps_image.n_active_rows + 3) / 4 * 4;
+    if (n_img_live > f0->n_image) n_img_live = f0->n_image;
+  }
   int slots[2] = {0, 0};
   if (f0->loss_slots) IMMOCO_TRY(immoco_fit_loss_slots(H, W, slots));
   const int per_iter = slots[0] + slots[1];
@@ -502,7 +517,7 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
       return IMMOCO_ERR_BAD_ARG;
   }
   auto zero_grads = [&](cudaStream_t st) {
-    for (int b = 0; b < B; ++b) cudaMemsetAsync(fs[b]->grads, 0, (size_t)(n_mot + f0->n_image) * sizeof(float), st);
+    for (int b = 0; b < B; ++b) cudaMemsetAsync(fs[b]->grads, 0, (size_t)(n_mot + n_img_live) * sizeof(float), st);
   };
 
   for (int it = it_begin; it < it_end; ++it) {
@@ -578,7 +593,8 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
     return 0;                                         \
   }()
     // ---- forward -------------------------------------------------------------------------------
-    K(0, is, EACH(immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is)));
+    K(0, is, EACH(taps_i ? immoco_hashgrid_fwd_taps(&f->grid_image, &f->taps_image, f->coords_image, pi + mlp_i, f->enc_image, P, is)
+                         : immoco_hashgrid_fwd(&f->grid_image, f->coords_image, pi + mlp_i, f->enc_image, P, is)));
     K(1, is, immoco_mlp_fwd_tc_batch(mi, P, wi, f0->act_image, 0, is));
     // gradient entropy needs the image only; it initialises d_image (lambda folded in)
     K(7, is, immoco_grad_entropy_batch(fb, lambdas_host[it], 0, H, W, is));
@@ -676,13 +692,14 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
     }
     K(12, is, EACH(immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
                                   gi + (int64_t)wi * 32, P, wi, f->act_image, is)));
-    K(13, is, EACH(immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is)));
+    K(13, is, EACH(taps_i ? immoco_hashgrid_bwd_taps(&f->grid_image, &f->taps_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is)
+                          : immoco_hashgrid_bwd(&f->grid_image, f->coords_image, f->d_enc_image, gi + mlp_i, P, is)));
     // ---- update (zero_grad fused), one launch per INR so each follows its own branch ---------------
     // (the LAST iteration of the call zeroes inside Adam, so the gradients are clean when the call returns)
     const int adam_zeroes = (defer_zero && it + 1 < it_end) ? 0 : 1;
     K(14, ms, M > 0 ? EACH(immoco_adam_step(pm, gm, f->exp_avg, f->exp_avg_sq, n_mot, f->lr, f->beta1, f->beta2,
                                             f->eps, it + 1, adam_zeroes, stream)) : nop());
-    K(15, is, EACH(immoco_adam_step(pi, gi, f->exp_avg + n_mot, f->exp_avg_sq + n_mot, f->n_image, f->lr,
+    K(15, is, EACH(immoco_adam_step(pi, gi, f->exp_avg + n_mot, f->exp_avg_sq + n_mot, n_img_live, f->lr,
                                     f->beta1, f->beta2, f->eps, it + 1, adam_zeroes, is)));
     if (!adam_zeroes) {
       cudaEventRecord(aux->adam_i_done, aux->stream);

@@ -35,6 +35,44 @@ __device__ __forceinline__ float2 load_row(const float2* p) {
 #endif
 }
 
+// Cache policy of the backward kernels (build-variant experiments, tools/l2_policy_ab.py):
+//  IMMOCO_HG_BWD_STREAM 1: the cotangent planes are read once -> streaming (evict-first) loads;
+//  IMMOCO_HG_RED_EVICT_LAST 1: the reductions carry an L2 evict-last policy, so the gradient table is still
+//  L2-resident when Adam reads it.
+#ifndef IMMOCO_HG_BWD_STREAM
+#define IMMOCO_HG_BWD_STREAM 0
+#endif
+#ifndef IMMOCO_HG_RED_EVICT_LAST
+#define IMMOCO_HG_RED_EVICT_LAST 0
+#endif
+__device__ __forceinline__ float2 load_cotangent(const float2* p) {
+#if IMMOCO_HG_BWD_STREAM
+  return __ldcs(p);
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void red_add(float2* p, float2 v) {
+#if IMMOCO_HG_RED_EVICT_LAST
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+  atomicAdd(p, v);
+#endif
+}
+__device__ __forceinline__ void red_add(float4* p, float4 v) {
+#if IMMOCO_HG_RED_EVICT_LAST
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+#else
+  atomicAdd(p, v);
+#endif
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreads)
 hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
@@ -100,7 +138,7 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
     uint32_t cell[D];
     float frac[D];
     if (valid) {
-      go = __ldg(d_enc + (size_t)level * n + i);
+      go = load_cotangent(d_enc + (size_t)level * n + i);
 #pragma unroll
       for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
     } else {
@@ -122,7 +160,7 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
       float vx = w * go.x, vy = w * go.y;
       if (hashed) {
         // one 64-bit vector reduction per corner (RED.ADD.F32x2)
-        if (live) atomicAdd(gtab + idx, make_float2(vx, vy));
+        if (live) red_add(gtab + idx, make_float2(vx, vy));
       } else {
         // contiguous runs of equal rows within the warp -> one reduction per run
         const uint32_t key = live ? idx : 0xFFFFFFFFu;
@@ -142,7 +180,7 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
           const float oy = __shfl_down_sync(0xffffffffu, vy, ofs);
           if (take) { vx += ox; vy += oy; }
         }
-        if (head && live) atomicAdd(gtab + idx, make_float2(vx, vy));
+        if (head && live) red_add(gtab + idx, make_float2(vx, vy));
       }
     }
   }
@@ -255,7 +293,7 @@ __device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, 
 #pragma unroll
     for (int d = 0; d < D; ++d) x[p][d] = 0.f;
     if (i < n) {
-      go[p] = __ldg(d_enc_level + i);
+      go[p] = load_cotangent(d_enc_level + i);
 #pragma unroll
       for (int d = 0; d < D; ++d) x[p][d] = __ldg(coords + (size_t)i * D + d);
     }
@@ -286,10 +324,10 @@ __device__ __forceinline__ void bwd_pair_item(const float* __restrict__ coords, 
       if (merge) {
         if (half == 0) {
           const float4 v = (idx & 1u) ? make_float4(ox, oy, vx, vy) : make_float4(vx, vy, ox, oy);
-          atomicAdd(reinterpret_cast<float4*>(gtab + (idx & ~1u)), v);
+          red_add(reinterpret_cast<float4*>(gtab + (idx & ~1u)), v);
         }
       } else {
-        atomicAdd(gtab + idx, make_float2(vx, vy));
+        red_add(gtab + idx, make_float2(vx, vy));
       }
     }
   }
@@ -312,6 +350,153 @@ hashgrid_bwd_pair_kernel(const __grid_constant__ immoco_grid_desc g, const float
     const float2* __restrict__ go = d_enc + (size_t)level * n;
     if ((entries & (entries - 1u)) == 0u) bwd_pair_item<D, kIdxHash>(coords, go, gtab, n, base, scale, res, entries, g.swizzle[level]);
     else bwd_pair_item<D, kIdxAny>(coords, go, gtab, n, base, scale, res, entries, 0u);
+  }
+}
+
+// ---- compact ("tap-indexed") storage of a grid's hashed levels ----------------------------------------------
+// The coordinates of a fit are constant, so the table rows a point touches can be looked up once
+// (hashgrid_tap_rows_kernel) and the hashed levels re-stored in ANY row order: the host ranks the rows by their
+// first touch in (level, point, corner) order (immoco.py:GridTaps).  What that buys on the 2-D image grid, whose
+// hashed levels are under-subscribed (102400 pixels x 4 corners into 2^19 rows: 53 % of the rows are ever touched):
+//  * rows nobody touches keep g = m = v = 0 for ever -- they are stored behind the touched ones and Adam / the
+//    gradient memset never visit them (C2: 5.59 M -> 3.11 M rows);
+//  * the rows a pixel touches first are consecutive, in pixel order: ~70 % of the gathers / reductions of a warp
+//    fall into a few adjacent lines instead of one line each.
+// The kernels read 16 bytes of row indices per (point, level) instead of hashing.
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+hashgrid_tap_rows_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                         uint32_t* __restrict__ rows, int n, int level0) {
+  const int level = level0 + blockIdx.y;
+  const float scale = g.scale[level];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    uint32_t cell[D];
+    float frac[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) grid_pos(__ldg(coords + (size_t)i * D + d), scale, cell[d], frac[d]);
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) {
+      uint32_t q[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) q[d] = cell[d] + (uint32_t)((c >> d) & 1);
+      rows[((size_t)blockIdx.y * n + i) * (1 << D) + c] =
+          grid_index<D>(q, g.hashed[level], g.entries[level], g.resolution[level], g.swizzle[level]);
+    }
+  }
+}
+
+// points per thread and item of the tap-indexed kernels (all index and row loads of an item are issued before
+// the first use)
+#ifndef IMMOCO_HG_TAP_PTS
+#define IMMOCO_HG_TAP_PTS 2
+#endif
+constexpr int kTapPts = IMMOCO_HG_TAP_PTS;
+
+// 2-D, one thread per point.  Same products and the same summation order as the lane-pair kernel (each dim-0
+// half: fma chain over the dim-1 corners; then half 0 + half 1), so the features are bit-identical to it.
+__device__ __forceinline__ void fwd_tap_item(const float2* __restrict__ coords, const float2* __restrict__ table,
+                                             const uint4* __restrict__ taps_level, float2* __restrict__ enc_level,
+                                             int n, int base, float scale) {
+  float2 v[kTapPts][4];
+  float2 x[kTapPts];
+#pragma unroll
+  for (int p = 0; p < kTapPts; ++p) {
+    const int i = base + p * kThreads + threadIdx.x;
+    x[p] = make_float2(0.f, 0.f);
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (i < n) { x[p] = __ldg(coords + i); t = __ldg(taps_level + i); }
+    if (i < n) {
+      v[p][0] = load_row(table + t.x); v[p][1] = load_row(table + t.y);
+      v[p][2] = load_row(table + t.z); v[p][3] = load_row(table + t.w);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[p][c] = make_float2(0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < kTapPts; ++p) {
+    const int i = base + p * kThreads + threadIdx.x;
+    uint32_t cell;
+    float f0, f1;
+    grid_pos(x[p].x, scale, cell, f0);
+    grid_pos(x[p].y, scale, cell, f1);
+    float2 half[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float w0 = h ? f0 : 1.0f - f0;
+      const float wa = w0 * (1.0f - f1), wb = w0 * f1;          // pair_weight: dim-1 corner 0, 1
+      half[h].x = fmaf(wb, v[p][2 + h].x, fmaf(wa, v[p][h].x, 0.f));
+      half[h].y = fmaf(wb, v[p][2 + h].y, fmaf(wa, v[p][h].y, 0.f));
+    }
+    if (i < n) enc_level[i] = make_float2(half[0].x + half[1].x, half[0].y + half[1].y);
+  }
+}
+
+// Forward of a grid with tap-indexed levels in ONE launch: items of the levels below `first` run the lane-pair
+// code, the others the indexed code; level-major order as in hashgrid_fwd_pair_kernel.
+__global__ void __launch_bounds__(kThreads, IMMOCO_HG_FWD_MIN_CTAS)
+hashgrid_fwd_taps_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                         const float2* __restrict__ table, const uint4* __restrict__ taps, float2* __restrict__ enc,
+                         int n, int first, int tiles_pair, int tiles_tap) {
+  pdl_wait();
+  const int items_pair = first * tiles_pair;
+  const int items = items_pair + (g.n_levels - first) * tiles_tap;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    if (item < items_pair) {
+      const int level = item / tiles_pair;
+      const int base = (item % tiles_pair) * (kPairPoints * kFwdPts);
+      const uint32_t entries = g.entries[level], hashed = g.hashed[level], res = g.resolution[level];
+      const float2* __restrict__ tab = table + g.offset[level];
+      float2* __restrict__ out = enc + (size_t)level * n;
+      const bool pow2 = (entries & (entries - 1u)) == 0u;
+      if (pow2 && hashed) fwd_pair_item<2, kIdxHash>(coords, tab, out, n, base, g.scale[level], res, entries, hashed, g.swizzle[level]);
+      else if (pow2) fwd_pair_item<2, kIdxDense>(coords, tab, out, n, base, g.scale[level], res, entries, hashed, 0u);
+      else fwd_pair_item<2, kIdxAny>(coords, tab, out, n, base, g.scale[level], res, entries, hashed, 0u);
+    } else {
+      const int k = (item - items_pair) / tiles_tap;
+      const int level = first + k;
+      const int base = ((item - items_pair) % tiles_tap) * (kThreads * kTapPts);
+      fwd_tap_item(reinterpret_cast<const float2*>(coords), table, taps + (size_t)k * n, enc + (size_t)level * n, n,
+                   base, g.scale[level]);
+    }
+  }
+}
+
+// Backward of the tap-indexed levels: one thread per point, four reductions; two rows that ended up in one
+// aligned 16-byte slot (consecutive first-touch ranks) go out as ONE RED.ADD.F32x4.
+__global__ void __launch_bounds__(kThreads)
+hashgrid_bwd_taps_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                         const float2* __restrict__ d_enc, const uint4* __restrict__ taps,
+                         float2* __restrict__ grad_table, int n, int first, int tiles) {
+  pdl_wait();
+  const int items = (g.n_levels - first) * tiles;
+  const float2* __restrict__ xy = reinterpret_cast<const float2*>(coords);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int k = item / tiles;
+    const int level = first + k;
+    const int i = (item % tiles) * kThreads + threadIdx.x;
+    if (i >= n) continue;
+    const float2 go = load_cotangent(d_enc + (size_t)level * n + i);
+    const float2 x = __ldg(xy + i);
+    const uint4 t = __ldg(taps + (size_t)k * n + i);
+    if (go.x == 0.0f && go.y == 0.0f) continue;                  // adding +-0 is a no-op
+    uint32_t cell;
+    float f0, f1;
+    grid_pos(x.x, g.scale[level], cell, f0);
+    grid_pos(x.y, g.scale[level], cell, f1);
+    const float wl = 1.0f - f0, wa = 1.0f - f1;
+    const float w[4] = {wl * wa, f0 * wa, wl * f1, f0 * f1};     // corner c: bit 0 = dim 0, bit 1 = dim 1
+    const uint32_t r[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int c = 0; c < 4; c += 2) {
+      const float ax = w[c] * go.x, ay = w[c] * go.y, bx = w[c + 1] * go.x, by = w[c + 1] * go.y;
+      if (r[c + 1] == r[c] + 1u && (r[c] & 1u) == 0u) {
+        red_add(reinterpret_cast<float4*>(grad_table + r[c]), make_float4(ax, ay, bx, by));
+      } else {
+        red_add(grad_table + r[c], make_float2(ax, ay));
+        red_add(grad_table + r[c + 1], make_float2(bx, by));
+      }
+    }
   }
 }
 
@@ -449,4 +634,65 @@ extern "C" int immoco_hashgrid_bwd_levels(const immoco_grid_desc* grid, const fl
                                           float* grad_table, int64_t n_points, int32_t level_begin,
                                           int32_t level_end, void* stream) {
   return run_bwd(grid, coords, d_enc, grad_table, n_points, level_begin, level_end, stream);
+}
+
+// ---- tap-indexed levels (see hashgrid_tap_rows_kernel) --------------------------------------------------------
+static int check_taps(const immoco_grid_desc* grid, const immoco_grid_taps* taps, int64_t n) {
+  if (int e = check(grid, n)) return e;
+  if (!taps || !taps->rows || taps->first_level < 0 || taps->first_level > grid->n_levels || taps->n_points != n)
+    return IMMOCO_ERR_BAD_ARG;
+  if (grid->n_dims != 2) return IMMOCO_ERR_UNSUPPORTED;
+  if (((uintptr_t)taps->rows & 15) != 0) return IMMOCO_ERR_BAD_ARG;
+  return 0;
+}
+
+extern "C" int immoco_hashgrid_tap_rows(const immoco_grid_desc* grid, const float* coords, int64_t n_points,
+                                        int32_t level_begin, int32_t level_end, uint32_t* rows, void* stream) {
+  if (int e = check(grid, n_points)) return e;
+  if (!coords || !rows || level_begin < 0 || level_end > grid->n_levels || level_begin > level_end) return IMMOCO_ERR_BAD_ARG;
+  if (n_points == 0 || level_begin == level_end) return 0;
+  const int n = (int)n_points;
+  dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(level_end - level_begin));
+  if (grid->n_dims == 2)
+    hashgrid_tap_rows_kernel<2><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, coords, rows, n, level_begin);
+  else
+    hashgrid_tap_rows_kernel<3><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, coords, rows, n, level_begin);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int immoco_hashgrid_fwd_taps(const immoco_grid_desc* grid, const immoco_grid_taps* taps, const float* coords,
+                                        const float* table, float* enc, int64_t n_points, void* stream) {
+  if (int e = check_taps(grid, taps, n_points)) return e;
+  if (n_points == 0) return 0;
+  const int n = (int)n_points;
+  const int first = taps->first_level;
+  const int tiles_pair = (int)ceil_div64(n, kPairPoints * kFwdPts);
+  const int tiles_tap = (int)ceil_div64(n, kThreads * kTapPts);
+  const int64_t items = (int64_t)first * tiles_pair + (int64_t)(grid->n_levels - first) * tiles_tap;
+  const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
+  const unsigned g = (unsigned)(items < cap ? items : cap);
+  immoco_launch(hashgrid_fwd_taps_kernel, dim3(g), dim3(kThreads), 0, (cudaStream_t)stream, *grid, coords,
+                (const float2*)table, (const uint4*)taps->rows, (float2*)enc, n, first, tiles_pair, tiles_tap);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int immoco_hashgrid_bwd_taps(const immoco_grid_desc* grid, const immoco_grid_taps* taps, const float* coords,
+                                        const float* d_enc, float* grad_table, int64_t n_points, void* stream) {
+  if (int e = check_taps(grid, taps, n_points)) return e;
+  if (n_points == 0) return 0;
+  const int first = taps->first_level;
+  if (int e = run_bwd(grid, coords, d_enc, grad_table, n_points, 0, first, stream)) return e;
+  if (first == grid->n_levels) return 0;
+  const int n = (int)n_points;
+  const int tiles = (int)ceil_div64(n, kThreads);
+  const int64_t items = (int64_t)tiles * (grid->n_levels - first);
+  const int per_sm = g_bwd_ctas_per_sm > 0 ? g_bwd_ctas_per_sm : g_ctas_per_sm;
+  const int64_t cap = per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * per_sm : items;
+  const unsigned g = (unsigned)(items < cap ? items : cap);
+  immoco_launch(hashgrid_bwd_taps_kernel, dim3(g), dim3(kThreads), 0, (cudaStream_t)stream, *grid, coords,
+                (const float2*)d_enc, (const uint4*)taps->rows, (float2*)grad_table, n, first, tiles);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
 }

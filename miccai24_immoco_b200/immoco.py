@@ -298,9 +298,90 @@ def _cached_csr(kind: str, shape, grid, swizzle, coords: torch.Tensor) -> GridCs
     return csr
 
 
+_TAPS_CACHE: dict = {}
+
+
+class GridTaps:
+    """Tap-indexed storage of a 2-D grid's hashed levels over one constant coordinate set (include/immoco_b200.h,
+    section 1c), built once per shape and shared by every fit of that shape.
+
+    ``immoco_hashgrid_tap_rows`` lists the row of every (level, point, corner); the rows of the hashed levels are
+    then ranked by their FIRST touch in that order.  ``perm[r]`` = physical row of reference-layout row r (the
+    identity below ``first_level``), ``rows`` = the physical rows of every tap, ``n_active_rows`` = rows that any
+    point touches (they come first; the others keep g = m = v = 0 for ever and are skipped by Adam)."""
+
+    def __init__(self, grid, desc, coords: torch.Tensor):
+        lib = nat.lib()
+        dev = coords.device
+        n = int(coords.shape[0])
+        first = grid.n_levels
+        while first > 0 and grid.hashed[first - 1] and (grid.entries[first - 1] & (grid.entries[first - 1] - 1)) == 0:
+            first -= 1
+        if grid.n_dims != 2 or first == grid.n_levels:
+            raise ValueError("tap-indexed storage needs a 2-D grid whose last levels are hashed")
+        self.first_level, self.n_points = first, n
+        n_lv = grid.n_levels - first
+        base = grid.offsets[first]
+        n_hashed_rows = grid.n_rows - base
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            raw = torch.empty((n_lv, n, 4), dtype=torch.int32, device=dev)
+            nat.check(lib.immoco_hashgrid_tap_rows(C.byref(desc), coords.data_ptr(), n, first, grid.n_levels,
+                                                   raw.data_ptr(), stream.cuda_stream), "hashgrid_tap_rows")
+            lvl_ofs = torch.tensor([grid.offsets[l] - base for l in range(first, grid.n_levels)], dtype=torch.int64,
+                                   device=dev)
+            key = (raw.to(torch.int64) + lvl_ofs[:, None, None]).reshape(-1)         # (level, point, corner) order
+            n_taps = key.numel()
+            first_touch = torch.full((n_hashed_rows,), n_taps, dtype=torch.int64, device=dev)
+            first_touch.scatter_reduce_(0, key, torch.arange(n_taps, dtype=torch.int64, device=dev), "amin")
+            order = torch.argsort(first_touch, stable=True)      # touched rows by first touch, then the others
+            phys = torch.empty_like(order)
+            phys[order] = torch.arange(n_hashed_rows, dtype=torch.int64, device=dev)
+            self.rows = (phys[key] + base).to(torch.int32).view(n_lv, n, 4).contiguous()
+            self.perm = torch.arange(grid.n_rows, dtype=torch.int64, device=dev)
+            self.perm[base:] = phys + base
+            # one host read per shape (cached): how many rows are live
+            self.n_active_rows = base + int((first_touch < n_taps).sum())
+            self.ready = torch.cuda.Event()
+            self.ready.record(stream)
+
+    def struct(self) -> nat.GridTaps:
+        t = nat.GridTaps()
+        t.rows = self.rows.data_ptr()
+        t.first_level = self.first_level
+        t.n_points = self.n_points
+        t.n_active_rows = self.n_active_rows
+        return t
+
+
+def _cached_taps(kind: str, shape, grid, coords: torch.Tensor) -> GridTaps:
+    key = (kind, tuple(int(v) for v in shape), str(coords.device), grid.n_dims, grid.offsets, grid.hashed)
+    taps = _TAPS_CACHE.get(key)
+    if taps is None:
+        taps = GridTaps(grid, grid.desc(), coords)
+        _TAPS_CACHE[key] = taps
+    torch.cuda.current_stream(coords.device).wait_event(taps.ready)
+    return taps
+
+
+def _taps_supported(grid) -> bool:
+    last = grid.n_levels - 1
+    return grid.n_dims == 2 and bool(grid.hashed[last]) and (grid.entries[last] & (grid.entries[last] - 1)) == 0
+
+
+def _taps_pay(grid, n_points: int) -> bool:
+    """Whether tap-indexed storage is expected to pay for ``n_points`` pixels: 4 n taps thrown into a level's
+    ``entries`` rows leave exp(-4 n / entries) of them untouched.  Measured on B200 (tools/taps_ab.py,
+    profiles/round2_tap_indexed_image_table.txt): 320 x 320 (47 % untouched) 621 -> 584 us per iteration;
+    640 x 368 (18 % untouched) 1390 -> 1410 us -- the indexed scatter issues more reductions than the lane-pair
+    kernel there (fewer aligned row pairs) and the shorter Adam pass no longer makes up for it."""
+    return _taps_supported(grid) and 4.0 * n_points <= 1.2 * grid.entries[grid.n_levels - 1]
+
+
 def clear_caches() -> None:
     """Drops the per-shape device caches (coordinates, row permutations, tap lists)."""
     _CSR_CACHE.clear()
+    _TAPS_CACHE.clear()
     _ROW_PERM_CACHE.clear()
     _COORD_CACHE.clear()
 
@@ -313,10 +394,16 @@ class FitEngine:
     The motion grid's hashed levels are stored in a permuted ROW LAYOUT (``GridSpec.row_swizzle``: both
     dim-0 corners of every lane pair in one 128-byte line; Adam is element-wise, so it does not care).
     Parameters are permuted on the way in (constructor, ``reset``) and back in ``write_back``; everything
-    outside the engine sees the reference's layout.  ``row_swizzle=False`` keeps the reference layout."""
+    outside the engine sees the reference's layout.  ``row_swizzle=False`` keeps the reference layout.
+
+    The image grid's hashed levels are stored TAP-INDEXED on the float-atomic path (``GridTaps``: rows ranked by
+    first touch, the never-touched 47 % of them at 320 x 320 behind the live ones where Adam and the gradient
+    memset do not go) whenever that is expected to pay (``_taps_pay``: at most ~70 % of the rows touched);
+    ``compact_image=False`` / ``True`` forces the reference layout / the indexed one."""
 
     def __init__(self, model: IMMoCo, max_iters: int, row_swizzle: bool = True,
-                 deterministic: Optional[bool] = None, fuse_adam: Optional[bool] = None):
+                 deterministic: Optional[bool] = None, fuse_adam: Optional[bool] = None,
+                 compact_image: Optional[bool] = None):
         """``deterministic`` (default: the library-wide ``immoco_get_deterministic()``): bit-reproducible fit --
         hash-grid backward as a row-sorted gather over a tap list built once per shape, MLP weight gradients
         as per-CTA blocks added in CTA order, image cotangent in 64-bit fixed point.  ``fuse_adam`` (default:
@@ -342,8 +429,14 @@ class FitEngine:
             if any(swz):
                 self._swizzle = swz
                 self._perm = _row_permutation(mot.grid, swz, dev)
+        self._n_mlp_image = img.mlp.n_params
+        self._taps: Optional[GridTaps] = None
+        want_taps = _taps_pay(img.grid, p) if compact_image is None else (bool(compact_image) and _taps_supported(img.grid))
+        if want_taps and not self.deterministic:
+            with torch.cuda.device(dev):
+                self._taps = _cached_taps("identity", (h, w), img.grid, model._ident)
         self._load_motion(mot.params.detach())
-        self.params[self.n_motion:].copy_(img.params.detach())
+        self._load_image(img.params.detach())
         self.state = torch.zeros((3, n), dtype=torch.float32, device=dev)   # grads, exp_avg, exp_avg_sq
         f32 = dict(dtype=torch.float32, device=dev)
         self.enc_image = torch.empty((16, p, 2), **f32)
@@ -408,34 +501,49 @@ class FitEngine:
             self.dc_max_bits = torch.zeros(max_iters, dtype=torch.int32, device=dev)
             f.d_image_fx = self.d_image_fx.data_ptr()
             f.dc_max_bits = self.dc_max_bits.data_ptr()
+        if self._taps is not None:
+            f.taps_image = self._taps.struct()
         self.fit = f
         self.launches = 0
 
     def set_kspace(self, k_in: torch.Tensor) -> None:
         self.k_in.copy_(torch.view_as_real(k_in.to(torch.complex64)))
 
-    def _load_motion(self, motion_params: torch.Tensor) -> None:
-        """Reference-layout motion parameters [W1 | W2 | table] -> the engine's (permuted-row) storage."""
-        dst = self.params[: self.n_motion]
-        if self._perm is None:
-            dst.copy_(motion_params)
+    @staticmethod
+    def _load(dst: torch.Tensor, src: torch.Tensor, k: int, perm: Optional[torch.Tensor]) -> None:
+        """Reference-layout INR parameters [W1 | W2 | table] -> the engine's (permuted-row) storage."""
+        if perm is None:
+            dst.copy_(src)
             return
-        k = self._n_mlp_motion
-        dst[:k].copy_(motion_params[:k])
-        dst[k:].view(-1, 2).index_copy_(0, self._perm, motion_params[k:].to(dst.device).view(-1, 2))
+        dst[:k].copy_(src[:k])
+        dst[k:].view(-1, 2).index_copy_(0, perm, src[k:].to(dst.device).view(-1, 2))
+
+    @staticmethod
+    def _unload(src: torch.Tensor, k: int, perm: Optional[torch.Tensor]) -> torch.Tensor:
+        if perm is None:
+            return src.clone()
+        return torch.cat([src[:k], src[k:].view(-1, 2)[perm].reshape(-1)])
+
+    def _load_motion(self, motion_params: torch.Tensor) -> None:
+        self._load(self.params[: self.n_motion], motion_params, self._n_mlp_motion, self._perm)
+
+    def _load_image(self, image_params: torch.Tensor) -> None:
+        self._load(self.params[self.n_motion:], image_params, self._n_mlp_image,
+                   None if self._taps is None else self._taps.perm)
 
     def motion_params(self) -> torch.Tensor:
         """The motion INR's parameters in the reference layout (a copy)."""
-        src = self.params[: self.n_motion]
-        if self._perm is None:
-            return src.clone()
-        k = self._n_mlp_motion
-        return torch.cat([src[:k], src[k:].view(-1, 2)[self._perm].reshape(-1)])
+        return self._unload(self.params[: self.n_motion], self._n_mlp_motion, self._perm)
+
+    def image_params(self) -> torch.Tensor:
+        """The image INR's parameters in the reference layout (a copy)."""
+        return self._unload(self.params[self.n_motion:], self._n_mlp_image,
+                            None if self._taps is None else self._taps.perm)
 
     def reset(self, image_params: torch.Tensor, motion_params: torch.Tensor) -> None:
         """Fresh instance: initial INR parameters, zero gradients / Adam moments / loss trace."""
         self._load_motion(motion_params)
-        self.params[self.n_motion:].copy_(image_params)
+        self._load_image(image_params)
         self.state.zero_()
         self.loss.zero_()
         if self.deterministic:
@@ -469,7 +577,7 @@ class FitEngine:
     def write_back(self) -> None:
         with torch.no_grad():
             self.model.motion_inr.params.copy_(self.motion_params())
-            self.model.image_inr.params.copy_(self.params[self.n_motion:])
+            self.model.image_inr.params.copy_(self.image_params())
 
 
 def run_batched(engines, lambdas: List[float], learning_rate: float, it_begin: int = 0,

@@ -298,6 +298,61 @@ def test_hashgrid_row_swizzle_equals_reference_layout(native_lib):
         assert float((enc - res["ref"][0]).norm() / res["ref"][0].norm()) < 1e-6
 
 
+@pytest.mark.parametrize("h,w", [(320, 320), (48, 40), (33, 17), (640, 368)])
+def test_hashgrid_tap_indexed_storage_equals_reference_layout(native_lib, h, w):
+    """2-D hash grid with its hashed levels stored tap-indexed (include/immoco_b200.h section 1c, immoco.py:GridTaps)
+    on a permuted table: features BIT-identical to the hashing kernels on the reference layout, table gradients
+    equal after un-permuting (float atomics: rounding), rows nobody touches stored behind the live ones."""
+    from miccai24_immoco_b200.immoco import GridTaps
+    gs = grid_spec(2, mb.encoding_config)
+    coords = mb.immoco._identity_grid(h, w, "cuda").view(-1, 2).contiguous()
+    n = coords.shape[0]
+    desc = gs.desc()
+    taps = GridTaps(gs, desc, coords)
+    first, base = taps.first_level, gs.offsets[taps.first_level]
+    assert first == 6 and taps.rows.shape == (16 - first, n, 4) and taps.rows.data_ptr() % 16 == 0
+    perm = taps.perm
+    assert torch.equal(torch.sort(perm).values, torch.arange(gs.n_rows, device="cuda"))        # a bijection ...
+    assert torch.equal(perm[:base], torch.arange(base, device="cuda"))                          # ... identity on the dense levels
+    # the tap list is the permuted image of the hash indices the kernels compute themselves
+    raw = torch.empty((16 - first, n, 4), dtype=torch.int32, device="cuda")
+    assert native_lib.immoco_hashgrid_tap_rows(C.byref(desc), coords.data_ptr(), n, first, 16, raw.data_ptr(), _s()) == 0
+    lvl = torch.tensor(gs.offsets[first:16], device="cuda")[:, None, None]
+    assert torch.equal(perm[raw.long() + lvl], taps.rows.long())
+    touched = torch.unique(raw.long() + lvl)
+    assert taps.n_active_rows == base + touched.numel()
+    assert int(perm[touched].max()) == taps.n_active_rows - 1                                   # live rows first, no holes
+    # ... ranked by first touch in (level, point, corner) order
+    assert int(taps.rows[0, 0, 0]) == base
+    g = torch.Generator().manual_seed(11)
+    table = ((torch.rand(gs.n_rows, 2, generator=g) - 0.5) * 1e-2).cuda()
+    d_enc = torch.randn(16, n, 2, generator=g).cuda()
+    d_enc[:, ::7] = 0.0                                          # zero cotangents are skipped
+    table_p = torch.empty_like(table)
+    table_p.index_copy_(0, perm, table)
+    t = taps.struct()
+    enc_ref, enc_tap = torch.empty(16, n, 2, device="cuda"), torch.empty(16, n, 2, device="cuda")
+    grad_ref, grad_tap = torch.zeros_like(table), torch.zeros_like(table)
+    s = _s()
+    assert native_lib.immoco_hashgrid_fwd(C.byref(desc), coords.data_ptr(), table.data_ptr(), enc_ref.data_ptr(), n, s) == 0
+    assert native_lib.immoco_hashgrid_bwd(C.byref(desc), coords.data_ptr(), d_enc.data_ptr(), grad_ref.data_ptr(), n, s) == 0
+    assert native_lib.immoco_hashgrid_fwd_taps(C.byref(desc), C.byref(t), coords.data_ptr(), table_p.data_ptr(),
+                                               enc_tap.data_ptr(), n, s) == 0
+    assert native_lib.immoco_hashgrid_bwd_taps(C.byref(desc), C.byref(t), coords.data_ptr(), d_enc.data_ptr(),
+                                               grad_tap.data_ptr(), n, s) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(enc_tap, enc_ref)
+    assert float((grad_tap[perm] - grad_ref).norm() / grad_ref.norm()) < 1e-6
+    assert float(grad_tap[taps.n_active_rows:].abs().max()) == 0.0 if taps.n_active_rows < gs.n_rows else True
+    # argument checks: 3-D grids and a tap list of another point count are rejected
+    gs3 = grid_spec(3, mb.encoding_config)
+    d3 = gs3.desc()
+    assert native_lib.immoco_hashgrid_fwd_taps(C.byref(d3), C.byref(t), coords.data_ptr(), table_p.data_ptr(),
+                                               enc_tap.data_ptr(), n, s) == nat.ERR_UNSUPPORTED
+    assert native_lib.immoco_hashgrid_fwd_taps(C.byref(desc), C.byref(t), coords.data_ptr(), table_p.data_ptr(),
+                                               enc_tap.data_ptr(), n - 1, s) == nat.ERR_BAD_ARG
+
+
 # ------------------------------------------------------------------------------------------------------------
 # deterministic building blocks (include/immoco_b200.h sections 1b, 2, 7)
 # ------------------------------------------------------------------------------------------------------------

@@ -430,6 +430,60 @@ def test_engine_row_swizzle_equals_reference_layout():
     assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < 1e-3
 
 
+@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (32, 32, 0)])
+def test_engine_tap_indexed_image_table_equals_reference_layout(h, w, n_mov):
+    """FitEngine with the image table's hashed levels stored tap-indexed (Adam and the gradient memset skip the rows no
+    pixel touches) vs compact_image=False: same forward bits, same losses and parameters (reference layout) after
+    three steps up to the rounding of float atomics; rows nobody touches never move and have clean moments."""
+    if n_mov > 0:
+        case = orc.make_case(h, w, n_mov, 1000)
+        masks, k = case["masks"].to(DEV), case["kspace_motion"]
+    else:
+        masks = torch.zeros((0, h, w), dtype=torch.long, device=DEV)
+        g = torch.Generator().manual_seed(5)
+        k = torch.complex(torch.randn(h, w, generator=g), torch.randn(h, w, generator=g))
+    model = mb.IMMoCo(masks)
+    p_img = model.image_inr.params.detach().clone()
+    p_mot = model.motion_inr.params.detach().clone()
+    if n_mov > 0:      # a displacement field of ~0.1 so the motion branch has real gradients
+        p_mot[2048:3072] *= 10.0
+        p_mot[3072:] *= 300.0
+    lam = mb.lambda_schedule(10, 1e-2)[:3]
+    assert mb.FitEngine(model, 3, deterministic=False)._taps is not None              # the default at these sizes
+    assert mb.FitEngine(model, 3, deterministic=True)._taps is None                   # the reproducible path has its own tap list
+    out = {}
+    for compact in (False, True):
+        eng = mb.FitEngine(model, 3, compact_image=compact, deterministic=False)
+        assert (eng._taps is not None) == compact
+        eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
+        eng.reset(p_img, p_mot)
+        assert torch.equal(eng.image_params(), p_img)              # in and out again: exact
+        eng.run(lam, 1e-2, 0, 1)
+        torch.cuda.synchronize()
+        first = (eng.k_out.clone(), eng.loss[0].clone())
+        eng.run(lam, 1e-2, 1, 3)
+        torch.cuda.synchronize()
+        assert float(eng.state[0].abs().max()) == 0.0               # gradients are clean when a call returns
+        out[compact] = first + (eng.image_params(), eng.loss_trace(lam), eng.motion_params())
+        if compact:
+            live = eng._n_mlp_image + 2 * eng._taps.n_active_rows
+            assert live < eng.n_image
+            assert float(eng.state[:, eng.n_motion + live:].abs().max()) == 0.0        # moments / gradients of dead rows
+            dead = torch.zeros(eng.n_image, dtype=torch.bool, device=DEV)            # reference-layout floats of dead rows
+            dead[eng._n_mlp_image:].view(-1, 2)[eng._taps.perm >= eng._taps.n_active_rows] = True
+            assert int(dead.sum()) == eng.n_image - live
+            assert torch.equal(out[True][2][dead], p_img[dead])     # dead rows: untouched, as under dense Adam
+            eng.write_back()
+            assert torch.equal(model.image_inr.params.detach(), out[True][2])
+    assert rel_l2(out[True][0], out[False][0]) < 1e-6               # the features are bit-identical; the row pass adds atomically
+    assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
+    assert np.allclose(out[True][3], out[False][3], rtol=1e-4)
+    assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < 1e-3
+    # (Adam's first steps are lr * sign(g): entries whose gradient is atomics-order noise may flip)
+    assert float(((out[True][4] - out[False][4]).abs() > 1e-3).float().mean()) < 5e-3
+    assert torch.equal(out[False][2][dead], p_img[dead])            # ... which is what the dense update does too
+
+
 def test_deferred_gradient_zeroing_equals_zeroing_in_adam():
     """immoco_fit_run zeroes the gradients with one memset on a third stream (Adam leaves them in place).  The
     loss trace must equal the run where Adam zeroes them itself -- a missed or late memset would accumulate

@@ -24,14 +24,15 @@ def test_library_loads_and_exports_every_declared_symbol(native_lib):
     assert declared == set(nat.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(native_lib, name) is not None
-    assert native_lib.immoco_abi_version() == 2
+    assert native_lib.immoco_abi_version() == 3
     assert native_lib.immoco_launches_per_iteration(4) == 16 and len(nat.PROFILE_SLOTS) == 16
     assert native_lib.immoco_launches_per_iteration_mode(4, 1, 0) == 17
     assert native_lib.immoco_launches_per_iteration_mode(4, 1, 1) == 15
     assert native_lib.immoco_launches_per_iteration_mode(0, 1, 1) == 10
-    sizes = (C.c_int32 * 4)()
+    sizes = (C.c_int32 * 5)()
     native_lib.immoco_struct_sizes(sizes)
-    assert tuple(sizes) == (C.sizeof(nat.GridDesc), C.sizeof(nat.Lines), C.sizeof(nat.Fit), C.sizeof(nat.GridCsr))
+    assert tuple(sizes) == (C.sizeof(nat.GridDesc), C.sizeof(nat.Lines), C.sizeof(nat.Fit), C.sizeof(nat.GridCsr),
+                            C.sizeof(nat.GridTaps))
     # the fp32 SIMT MLP kernels are test-side only (tests/checkers), not in the product library
     assert not hasattr(native_lib, "immoco_set_mlp_impl") and "mlp.cu" not in nat.SOURCES
     assert native_lib.immoco_get_deterministic() in (0, 1)

@@ -36,7 +36,7 @@ if __name__ == "__main__":
                 k = case["kspace_motion"]
                 eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
                 engines.append(eng)
-            inits = [(e.params[e.n_motion:].clone(), e.motion_params()) for e in engines]
+            inits = [(e.image_params(), e.motion_params()) for e in engines]
             mb.run_batched(engines, lam, 1e-2, 0, min(20, a.iters))
             torch.cuda.synchronize()
             best = 1e9

@@ -28,7 +28,7 @@ if __name__ == "__main__":
             model = mb.IMMoCo(case["masks"].cuda())
             eng = mb.FitEngine(model, a.iters)
             eng.set_kspace((k / k.abs().max() * 16000).cuda())
-            p_i, p_m = eng.params[eng.n_motion:].clone(), eng.motion_params()
+            p_i, p_m = eng.image_params(), eng.motion_params()
             eng.run(lam, 1e-2, 0, 20)
             torch.cuda.synchronize()
             best = 1e9
