@@ -146,6 +146,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def live_image_params(eng) -> int:
+    """Image-INR parameters one Adam launch reads and writes (FitEngine: MLP block + the table rows some pixel touches
+    when the hashed levels are stored tap-indexed, everything otherwise)."""
+    taps = getattr(eng, "_taps", None)
+    if taps is None:
+        return eng.n_image
+    return min(eng.n_image, (eng._n_mlp_image + 2 * taps.n_active_rows + 3) // 4 * 4)
+
+
 def algorithmic_bytes(slot: str, p: int, m: int, n_par, t_img: int, t_mot: int) -> float:
     """Algorithmic bytes per launch of each kernel of one iteration (sums to
     SURVEY 8(d)'s B_iter = 28 N_par + 16 (T_img + T_mot) + 64 P (M+1) plus the feature planes the
@@ -353,7 +362,8 @@ def run_c2(args):
         im, _ = mb.imcoco_motion_correction(k_host[j], masks_host[j], iters, 1e-2, 1e-2, False, deterministic=det)
         return im.cpu()
 
-    n_par2 = (models[0].motion_inr.n_params, models[0].image_inr.n_params)
+    # parameters Adam actually visits: with the image table stored tap-indexed the rows no pixel touches are skipped
+    n_par2 = (models[0].motion_inr.n_params, live_image_params(engines[0]))
     engines.clear()        # free the resident engines' HBM before the API path allocates its own
     n_e2e = max(1, min(args.steps, args.e2e_steps))
     step_e2e(0)
@@ -510,7 +520,7 @@ def run_stack(args):
         ms_sum = (C.c_float * len(nat.PROFILE_SLOTS))()
         n_prof = lib.immoco_profile_read(prof, ms_sum)
         lib.immoco_profile_destroy(prof)
-        n_par2 = (model.motion_inr.n_params, model.image_inr.n_params)
+        n_par2 = (model.motion_inr.n_params, live_image_params(eng))
         t_img, t_mot = touched_rows(orc, torch, h, w, n_mov)
         per_rank = (step_slices + world - 1) // world
         ms_per_iter = ms_total / (args.steps * per_rank * iters)

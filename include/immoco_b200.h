@@ -52,7 +52,17 @@ typedef struct immoco_grid_desc {
    * + 1) into the low bits, so both corners of every lane pair lie in one 128-byte line.
    * Used for power-of-two hashed levels only; ignored elsewhere. */
   uint32_t swizzle[IMMOCO_MAX_LEVELS];
+  /* swizzle[l] == IMMOCO_LAYOUT_LUT: the row of hash index r is an ARBITRARY linear bijection S_l on the index
+   * bits, given as chunk tables: S_l(r) = T[r & 127] ^ T[128 + ((r >> 7) & 63)] ^ T[192 + ((r >> 13) & 63)],
+   * T = layout_lut + 256 * l (device memory, 256 words per level; entries <= 2^19).  Built by
+   * miccai24_immoco_b200/encoding.py:GridSpec.linear_layout so that the 2 M rows ONE pixel corner needs over all M
+   * movement groups and both dim-0 corners fall into one or two 128-byte lines; the grouped kernels
+   * (immoco_hashgrid_fwd_grouped / _bwd_grouped) put those 2 M rows on adjacent lanes.  The generic entry points
+   * honour the tables through their one-thread-per-point kernels (checkers); the row-sorted (csr) and the fused
+   * MLP-scatter entry points reject such descriptors. */
+  const uint32_t* layout_lut;
 } immoco_grid_desc;
+#define IMMOCO_LAYOUT_LUT 0xFFFFFFFFu
 
 /* Column structure of the movement-group masks (src/utils/motion_utils.py:56-109 produces masks
  * that are constant along rows): K[:,l] = static_w[l]*F(I)[:,l] + sum_m w_ml * F(I_m)[:,l].   */
@@ -80,6 +90,16 @@ int immoco_hashgrid_fwd_levels(const immoco_grid_desc* grid, const float* coords
 int immoco_hashgrid_bwd_levels(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
                                float* grad_table, int64_t n_points, int32_t level_begin,
                                int32_t level_end, void* stream);
+/* The same two passes for a GROUPED 3-D coordinate set: coords[(g * n_pixels + p) * 3 ..] = (t_g, y_p, x_p) -- the
+ * first coordinate depends on the group only, the other two on the pixel only (make_grids((M, H, W)),
+ * src/models/immoco.py:48-53,78-80).  The 2 M lanes of a "bundle" take the M groups x 2 dim-0 corners of one pixel, so
+ * one gather / reduction instruction touches every 128-byte line that holds rows of that pixel corner once for ALL
+ * groups (with an IMMOCO_LAYOUT_LUT layout: 2 lines instead of 4 at M = 4).  n_groups must be 2, 4, 8 or 16
+ * (IMMOCO_ERR_UNSUPPORTED otherwise).  Features bit-identical to immoco_hashgrid_fwd on the same table. */
+int immoco_hashgrid_fwd_grouped(const immoco_grid_desc* grid, const float* coords, const float* table, float* enc,
+                                int64_t n_pixels, int32_t n_groups, void* stream);
+int immoco_hashgrid_bwd_grouped(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
+                                float* grad_table, int64_t n_pixels, int32_t n_groups, void* stream);
 /* Kernel selection for A/B checks: 1 = lane-pair kernels (two adjacent lanes take the two dim-0
  * corners of one point; product path), 0 = one thread per (point, level). Same results to rounding. */
 int immoco_set_hashgrid_impl(int32_t pair);

@@ -20,6 +20,7 @@ SOURCES = ["hashgrid.cu", "hashgrid_csr.cu", "mlp_tc.cu", "forward_model.cu", "f
 MAX_LEVELS = 16
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 ERR_BAD_ARG, ERR_UNSUPPORTED = -1, -2
+LAYOUT_LUT = 0xFFFFFFFF
 PROFILE_SLOTS = ["hashgrid_fwd_image", "mlp_fwd_image", "hashgrid_fwd_motion", "mlp_fwd_motion", "fft_rows",
                  "motion_rows_fwd", "colpass_loss", "grad_entropy", "fft_rows_adj", "motion_rows_bwd",
                  "mlp_bwd_motion", "hashgrid_bwd_motion", "mlp_bwd_image", "hashgrid_bwd_image", "adam_motion",
@@ -36,6 +37,7 @@ class GridDesc(C.Structure):
         ("offset", C.c_uint32 * (MAX_LEVELS + 1)),
         ("hashed", C.c_uint32 * MAX_LEVELS),
         ("swizzle", C.c_uint32 * MAX_LEVELS),
+        ("layout_lut", C.c_void_p),
     ]
 
 
@@ -112,6 +114,8 @@ _SIGNATURES = {
     "immoco_hashgrid_bwd_csr": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P]),
     "immoco_hashgrid_bwd_csr_adam": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridCsr), _P, _P, _P, _P, _P, C.c_double,
                                                C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
+    "immoco_hashgrid_fwd_grouped": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "immoco_hashgrid_bwd_grouped": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "immoco_hashgrid_tap_rows": (C.c_int, [C.POINTER(GridDesc), _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "immoco_hashgrid_fwd_taps": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridTaps), _P, _P, _P, C.c_int64, _P]),
     "immoco_hashgrid_bwd_taps": (C.c_int, [C.POINTER(GridDesc), C.POINTER(GridTaps), _P, _P, _P, C.c_int64, _P]),

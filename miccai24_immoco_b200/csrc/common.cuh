@@ -74,6 +74,21 @@ __host__ __device__ __forceinline__ uint32_t grid_swizzle(uint32_t r, uint32_t s
   return r ^ ((x << a) | (x << b));
 }
 
+// physical row of hash index r under a level's chunk tables (immoco_grid_desc::layout_lut): S is linear over the
+// index bits, so it is the XOR of the images of three bit groups
+__host__ __device__ __forceinline__ uint32_t grid_lut_row(const uint32_t* t, uint32_t r) {
+  return t[r & 127u] ^ t[128u + ((r >> 7) & 63u)] ^ t[192u + ((r >> 13) & 63u)];
+}
+// the level's chunk tables when the descriptor stores the level under a general linear layout, else nullptr
+__host__ __device__ __forceinline__ const uint32_t* grid_level_lut(const immoco_grid_desc& g, int level) {
+  return (g.swizzle[level] == IMMOCO_LAYOUT_LUT && g.layout_lut) ? g.layout_lut + 256 * level : nullptr;
+}
+inline bool grid_has_lut(const immoco_grid_desc& g) {
+  for (int l = 0; l < g.n_levels; ++l)
+    if (g.swizzle[l] == IMMOCO_LAYOUT_LUT) return true;
+  return false;
+}
+
 template <int D>
 __host__ __device__ __forceinline__ uint32_t grid_index(const uint32_t (&q)[D], uint32_t hashed,
                                                         uint32_t entries, uint32_t res, uint32_t swz = 0u) {

@@ -467,6 +467,7 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
     if ((f->loss_slots == nullptr) != (f0->loss_slots == nullptr)) return IMMOCO_ERR_BAD_ARG;
     // tap-indexed image table: all fits of a batch share the shape, hence the tap list and the live-row count
     if ((f->taps_image.rows == nullptr) != (f0->taps_image.rows == nullptr)) return IMMOCO_ERR_BAD_ARG;
+    if (grid_has_lut(f->grid_motion) != grid_has_lut(f0->grid_motion)) return IMMOCO_ERR_BAD_ARG;
     if (!det && f->taps_image.rows &&
         (f->taps_image.n_points != (int64_t)H * W || f->taps_image.n_active_rows != f0->taps_image.n_active_rows ||
          f->taps_image.n_active_rows < 0 || f->taps_image.n_active_rows > (int64_t)f->grid_image.offset[f->grid_image.n_levels]))
@@ -487,6 +488,10 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
   // floats of the image INR that Adam and the gradient memset visit: everything, or (tap-indexed table) the MLP
   // block + the rows some pixel touches, rounded up to a 128-bit item
   const bool taps_i = !det && f0->taps_image.rows != nullptr;
+  // motion table under a chunk-table layout (immoco_grid_desc::layout_lut): the grouped kernels, which rely on
+  // coords_motion being (t_g, y_p, x_p) -- what make_grids((M, H, W)) produces (src/models/immoco.py:48-53)
+  const bool grouped_m = M > 0 && grid_has_lut(f0->grid_motion);
+  if (grouped_m && (det || g_fused_scatter)) return IMMOCO_ERR_UNSUPPORTED;
   int64_t n_img_live = f0->n_image;
   if (taps_i) {
     n_img_live = (mlp_i + 2 * f0->taps_image.n_active_rows + 3) / 4 * 4;
@@ -599,7 +604,8 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
     // gradient entropy needs the image only; it initialises d_image (lambda folded in)
     K(7, is, immoco_grad_entropy_batch(fb, lambdas_host[it], 0, H, W, is));
     if (two) cudaEventRecord(aux->join_fwd, aux->stream);
-    K(2, ms, M > 0 ? EACH(immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream)) : nop());
+    K(2, ms, M > 0 ? EACH(grouped_m ? immoco_hashgrid_fwd_grouped(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, P, M, stream)
+                                    : immoco_hashgrid_fwd(&f->grid_motion, f->coords_motion, pm + mlp_m, f->enc_motion, MP, stream)) : nop());
     if (defer_zero && zero_pending) {
       // gradients of the previous iteration were consumed by both Adam launches (Adam_m precedes this point
       // on `ms`, Adam_i is awaited through its event): zero them now, beside the SM-bound kernels that follow
@@ -688,7 +694,8 @@ static int fit_run_impl(const immoco_fit* const* fs, int B, int32_t it_begin, in
       K(10, ms, M > 0 ? EACH(immoco_mlp_bwd(f->enc_motion, pm, pm + (int64_t)wm * 32, f->d_disp, f->d_enc_motion, gm,
                                             gm + (int64_t)wm * 32, MP, wm, f->act_motion, stream)) : nop());
       if (two) { cudaEventRecord(aux->mlp_done, ms); cudaStreamWaitEvent(aux->stream, aux->mlp_done, 0); }
-      K(11, ms, M > 0 ? EACH(immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream)) : nop());
+      K(11, ms, M > 0 ? EACH(grouped_m ? immoco_hashgrid_bwd_grouped(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, P, M, stream)
+                                       : immoco_hashgrid_bwd(&f->grid_motion, f->coords_motion, f->d_enc_motion, gm + mlp_m, MP, stream)) : nop());
     }
     K(12, is, EACH(immoco_mlp_bwd(f->enc_image, pi, pi + (int64_t)wi * 32, f->d_image, f->d_enc_image, gi,
                                   gi + (int64_t)wi * 32, P, wi, f->act_image, is)));

@@ -83,7 +83,8 @@ hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
   const uint32_t res = g.resolution[level];
   const uint32_t entries = g.entries[level];
   const uint32_t hashed = g.hashed[level];
-  const uint32_t swz = g.swizzle[level];
+  const uint32_t* __restrict__ lut = grid_level_lut(g, level);       // general linear layout: tables read from global memory
+  const uint32_t swz = lut ? 0u : g.swizzle[level];
   const float2* __restrict__ tab = table + g.offset[level];
 
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -104,7 +105,9 @@ hashgrid_fwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
         // same association order as the oracle: w = w0 * w1 * w2
         w = (d == 0) ? (bit ? frac[0] : 1.0f - frac[0]) : w * (bit ? frac[d] : 1.0f - frac[d]);
       }
-      const float2 v = __ldg(tab + grid_index<D>(q, hashed, entries, res, swz));
+      uint32_t row = grid_index<D>(q, hashed, entries, res, swz);
+      if (lut) row = grid_lut_row(lut, row);
+      const float2 v = __ldg(tab + row);
       acc.x = fmaf(w, v.x, acc.x);
       acc.y = fmaf(w, v.y, acc.y);
     }
@@ -127,7 +130,8 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
   const uint32_t res = g.resolution[level];
   const uint32_t entries = g.entries[level];
   const uint32_t hashed = g.hashed[level];
-  const uint32_t swz = g.swizzle[level];
+  const uint32_t* __restrict__ lut = grid_level_lut(g, level);
+  const uint32_t swz = lut ? 0u : g.swizzle[level];
   float2* __restrict__ gtab = grad_table + g.offset[level];
   const unsigned lane = threadIdx.x & 31u;
 
@@ -156,7 +160,8 @@ hashgrid_bwd_kernel(const __grid_constant__ immoco_grid_desc g, const float* __r
         q[d] = cell[d] + (uint32_t)bit;
         w = (d == 0) ? (bit ? frac[0] : 1.0f - frac[0]) : w * (bit ? frac[d] : 1.0f - frac[d]);
       }
-      const uint32_t idx = grid_index<D>(q, hashed, entries, res, swz);
+      uint32_t idx = grid_index<D>(q, hashed, entries, res, swz);
+      if (lut) idx = grid_lut_row(lut, idx);
       float vx = w * go.x, vy = w * go.y;
       if (hashed) {
         // one 64-bit vector reduction per corner (RED.ADD.F32x2)
@@ -379,8 +384,9 @@ hashgrid_tap_rows_kernel(const __grid_constant__ immoco_grid_desc g, const float
       uint32_t q[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) q[d] = cell[d] + (uint32_t)((c >> d) & 1);
-      rows[((size_t)blockIdx.y * n + i) * (1 << D) + c] =
-          grid_index<D>(q, g.hashed[level], g.entries[level], g.resolution[level], g.swizzle[level]);
+      const uint32_t* lut = grid_level_lut(g, level);
+      const uint32_t row = grid_index<D>(q, g.hashed[level], g.entries[level], g.resolution[level], lut ? 0u : g.swizzle[level]);
+      rows[((size_t)blockIdx.y * n + i) * (1 << D) + c] = lut ? grid_lut_row(lut, row) : row;
     }
   }
 }
@@ -500,6 +506,202 @@ hashgrid_bwd_taps_kernel(const __grid_constant__ immoco_grid_desc g, const float
   }
 }
 
+// ---- grouped ("bundle") kernels of the 3-D grid -----------------------------------------------------------------
+// Coordinates (t_g, y_p, x_p): the 2 M lanes of a bundle take the M groups x 2 dim-0 corners of ONE pixel.  The hash
+// is XOR-linear and so is the row layout S (Gray/exchange word or chunk tables), hence
+//     row(corner) = S(q0) ^ S((c1 + b1) * P1) ^ S((c2 + b2) * P2):
+// S(q0) is a per-lane constant of the item (the group's cell), the four pixel terms are evaluated once per BUNDLE
+// (lanes 0..3, three shared-memory look-ups each) and broadcast.  With encoding.py:linear_layout the 2 M rows of a
+// pixel corner lie in one or two 128-byte lines, so a gather / reduction instruction of a warp touches 8 lines
+// (M = 4) instead of the lane-pair kernels' 16: the L1TEX tag stage (one line per cycle and SM) is what paces the
+// gathers.  Same products and summation order as the lane-pair kernels: bit-identical features.
+// pixel passes per item: an item pays the table staging (a global load + two barriers) and the per-lane group
+// constants once.  B200, 3-D grid at C2 (tools/grouped_ab.py, gpurun_out/r305 / r306): forward 2 -> 108 us,
+// 4 -> 90 us, 8 -> 84 us; resident CTAs per SM the forward kernel is compiled for: 4 (64 registers) -> 98 us,
+// 6 (40) -> 90 us, 8 (32, spills) -> 106 us
+#ifndef IMMOCO_HG_BUNDLE_ITERS
+#define IMMOCO_HG_BUNDLE_ITERS 8
+#endif
+#ifndef IMMOCO_HG_BUNDLE_ITERS_BWD
+#define IMMOCO_HG_BUNDLE_ITERS_BWD 4
+#endif
+constexpr int kBundleIters = IMMOCO_HG_BUNDLE_ITERS;
+constexpr int kBundleItersBwd = IMMOCO_HG_BUNDLE_ITERS_BWD;
+#ifndef IMMOCO_HG_BUNDLE_MIN_CTAS
+#define IMMOCO_HG_BUNDLE_MIN_CTAS 6
+#endif
+
+struct BundleLevel {
+  uint32_t mask, swz, res, entries, hashed;
+  bool lin;           // hashed power-of-two level: XOR-linear index + linear layout
+  bool lut;
+};
+
+__device__ __forceinline__ uint32_t bundle_layout(const BundleLevel& lv, const uint32_t* lut_s, uint32_t x) {
+  return lv.lut ? grid_lut_row(lut_s, x) : grid_swizzle(x, lv.swz);
+}
+
+// rows of the four (dim-1, dim-2) corners of this lane's (group, dim-0 corner) for one pixel
+__device__ __forceinline__ void bundle_rows(const BundleLevel& lv, const uint32_t* lut_s, uint32_t q0, uint32_t s0,
+                                            uint32_t c1, uint32_t c2, int lb, unsigned lead, uint32_t (&row)[4]) {
+  if (lv.lin) {
+    // lane lb & 3 of the bundle evaluates one of the four pixel terms
+    const uint32_t term = (lb & 2) ? (c2 + (uint32_t)(lb & 1)) * 805459861u : (c1 + (uint32_t)(lb & 1)) * 2654435761u;
+    const uint32_t s = lb < 4 ? bundle_layout(lv, lut_s, term & lv.mask) : 0u;     // fewer active lanes: fewer bank conflicts
+    const uint32_t a0 = __shfl_sync(0xffffffffu, s, lead), a1 = __shfl_sync(0xffffffffu, s, lead + 1);
+    const uint32_t b0 = __shfl_sync(0xffffffffu, s, lead + 2), b1 = __shfl_sync(0xffffffffu, s, lead + 3);
+    row[0] = s0 ^ a0 ^ b0; row[1] = s0 ^ a1 ^ b0; row[2] = s0 ^ a0 ^ b1; row[3] = s0 ^ a1 ^ b1;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t q[3] = {q0, c1 + (uint32_t)(c & 1), c2 + (uint32_t)(c >> 1)};
+      row[c] = grid_index<3>(q, lv.hashed, lv.entries, lv.res, 0u);
+    }
+  }
+}
+
+__device__ __forceinline__ BundleLevel bundle_level(const immoco_grid_desc& g, int level) {
+  BundleLevel lv;
+  lv.entries = g.entries[level]; lv.mask = lv.entries - 1u; lv.res = g.resolution[level]; lv.hashed = g.hashed[level];
+  lv.lin = lv.hashed != 0u && (lv.entries & lv.mask) == 0u;
+  lv.lut = lv.lin && g.swizzle[level] == IMMOCO_LAYOUT_LUT && g.layout_lut != nullptr;
+  lv.swz = (lv.lin && !lv.lut) ? g.swizzle[level] : 0u;
+  return lv;
+}
+
+__global__ void __launch_bounds__(kThreads, IMMOCO_HG_BUNDLE_MIN_CTAS)
+hashgrid_fwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                           const float2* __restrict__ table, float2* __restrict__ enc, int P, int M, int level0,
+                           int n_levels, int tiles) {
+  __shared__ uint32_t lut_s[256];
+  pdl_wait();
+  const int lanes = 2 * M, bundles = kThreads / lanes;
+  const int lb = threadIdx.x % lanes, bundle = threadIdx.x / lanes;
+  const int grp = lb >> 1, half = lb & 1;
+  const unsigned lead = (threadIdx.x & 31u) & ~(unsigned)(lanes - 1);
+  const size_t n = (size_t)P * M;
+  const float t_g = __ldg(coords + (size_t)grp * P * 3);
+  for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
+    const int level = level0 + item / tiles;
+    const int pix0 = (item % tiles) * (bundles * kBundleIters);
+    const BundleLevel lv = bundle_level(g, level);
+    const float scale = g.scale[level];
+    __syncthreads();
+    if (lv.lut) lut_s[threadIdx.x] = __ldg(g.layout_lut + 256 * level + threadIdx.x);
+    __syncthreads();
+    uint32_t c0;
+    float f0;
+    grid_pos(t_g, scale, c0, f0);
+    const uint32_t q0 = c0 + (uint32_t)half;
+    const uint32_t s0 = lv.lin ? bundle_layout(lv, lut_s, q0 & lv.mask) : 0u;
+    const float w0 = half ? f0 : 1.0f - f0;
+    const float2* __restrict__ tab = table + g.offset[level];
+    float2* __restrict__ out = enc + (size_t)level * n + (size_t)grp * P;
+#pragma unroll
+    for (int it = 0; it < kBundleIters; it += 2) {
+      float2 v[2][4];
+      float fr[2][3];
+      int pix[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        pix[p] = pix0 + (it + p) * bundles + bundle;
+        const bool ok = pix[p] < P;
+        const float y = ok ? __ldg(coords + (size_t)pix[p] * 3 + 1) : 0.f;
+        const float x = ok ? __ldg(coords + (size_t)pix[p] * 3 + 2) : 0.f;
+        uint32_t c1, c2, row[4];
+        grid_pos(y, scale, c1, fr[p][1]);
+        grid_pos(x, scale, c2, fr[p][2]);
+        fr[p][0] = f0;
+        bundle_rows(lv, lut_s, q0, s0, c1, c2, lb, lead, row);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[p][c] = ok ? load_row(tab + row[c]) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float w = pair_weight<3>(fr[p], w0, c);
+          acc.x = fmaf(w, v[p][c].x, acc.x);
+          acc.y = fmaf(w, v[p][c].y, acc.y);
+        }
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+        if (pix[p] < P && half == 0) out[pix[p]] = acc;
+      }
+    }
+  }
+}
+
+// hashed power-of-two levels only (the dense levels keep the run-aggregating kernel)
+__global__ void __launch_bounds__(kThreads)
+hashgrid_bwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const float* __restrict__ coords,
+                           const float2* __restrict__ d_enc, float2* __restrict__ grad_table, int P, int M,
+                           int level0, int n_levels, int tiles) {
+  __shared__ uint32_t lut_s[256];
+  pdl_wait();
+  const int lanes = 2 * M, bundles = kThreads / lanes;
+  const int lb = threadIdx.x % lanes, bundle = threadIdx.x / lanes;
+  const int grp = lb >> 1, half = lb & 1;
+  const unsigned lead = (threadIdx.x & 31u) & ~(unsigned)(lanes - 1);
+  const size_t n = (size_t)P * M;
+  const float t_g = __ldg(coords + (size_t)grp * P * 3);
+  for (int item = blockIdx.x; item < n_levels * tiles; item += gridDim.x) {
+    const int level = level0 + item / tiles;
+    const int pix0 = (item % tiles) * (bundles * kBundleItersBwd);
+    const BundleLevel lv = bundle_level(g, level);
+    const float scale = g.scale[level];
+    __syncthreads();
+    if (lv.lut) lut_s[threadIdx.x] = __ldg(g.layout_lut + 256 * level + threadIdx.x);
+    __syncthreads();
+    uint32_t c0;
+    float f0;
+    grid_pos(t_g, scale, c0, f0);
+    const uint32_t q0 = c0 + (uint32_t)half;
+    const uint32_t s0 = bundle_layout(lv, lut_s, q0 & lv.mask);
+    const float w0 = half ? f0 : 1.0f - f0;
+    // the pair's rows differ by S(cell ^ (cell + 1)); == 1: one aligned 16-byte slot -> ONE RED.ADD.F32x4 by the even lane
+    const bool merge = (s0 ^ __shfl_xor_sync(0xffffffffu, s0, 1)) == 1u;
+    float2* __restrict__ gtab = grad_table + g.offset[level];
+    const float2* __restrict__ go_l = d_enc + (size_t)level * n + (size_t)grp * P;
+#pragma unroll 2
+    for (int it = 0; it < kBundleItersBwd; ++it) {
+      const int pix = pix0 + it * bundles + bundle;
+      const bool ok = pix < P;
+      float2 go = make_float2(0.f, 0.f);
+      float y = 0.f, x = 0.f;
+      if (ok) {
+        go = load_cotangent(go_l + pix);
+        y = __ldg(coords + (size_t)pix * 3 + 1);
+        x = __ldg(coords + (size_t)pix * 3 + 2);
+      }
+      float fr[3];
+      uint32_t c1, c2, row[4];
+      grid_pos(y, scale, c1, fr[1]);
+      grid_pos(x, scale, c2, fr[2]);
+      fr[0] = f0;
+      bundle_rows(lv, lut_s, q0, s0, c1, c2, lb, lead, row);
+      const bool live = !(go.x == 0.0f && go.y == 0.0f);       // adding +-0 is a no-op (also covers pix >= P)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float w = pair_weight<3>(fr, w0, c);
+        const float vx = w * go.x, vy = w * go.y;
+        const float ox = __shfl_xor_sync(0xffffffffu, vx, 1);
+        const float oy = __shfl_xor_sync(0xffffffffu, vy, 1);
+        if (!live) continue;
+        if (merge) {
+          if (half == 0) {
+            const float4 v = (row[c] & 1u) ? make_float4(ox, oy, vx, vy) : make_float4(vx, vy, ox, oy);
+            red_add(reinterpret_cast<float4*>(gtab + (row[c] & ~1u)), v);
+          }
+        } else {
+          red_add(gtab + row[c], make_float2(vx, vy));
+        }
+      }
+    }
+  }
+}
+
 int check(const immoco_grid_desc* g, int64_t n) {
   if (!g || n < 0 || n > (int64_t)0x7fffffff / 2) return IMMOCO_ERR_BAD_ARG;
   if (g->n_levels < 1 || g->n_levels > IMMOCO_MAX_LEVELS) return IMMOCO_ERR_BAD_ARG;
@@ -533,7 +735,7 @@ static int run_fwd(const immoco_grid_desc* grid, const float* coords, const floa
   if (n_points == 0 || l0 == l1) return 0;
   const int n = (int)n_points;
   cudaStream_t s = (cudaStream_t)stream;
-  if (g_pair) {
+  if (g_pair && !grid_has_lut(*grid)) {
     const int tiles = (int)ceil_div64(n, kPairPoints * kFwdPts);
     const int64_t items = (int64_t)tiles * (l1 - l0);
     const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
@@ -563,8 +765,9 @@ static int run_bwd(const immoco_grid_desc* grid, const float* coords, const floa
   // consecutive levels of one kind (dense: run-aggregating kernel, hashed: lane-pair kernel) per launch
   for (int a = l0; a < l1;) {
     int b = a + 1;
-    const bool pair = g_pair && grid->hashed[a];
-    while (b < l1 && (g_pair && grid->hashed[b]) == pair) ++b;
+    const bool use_pair = g_pair && !grid_has_lut(*grid);
+    const bool pair = use_pair && grid->hashed[a];
+    while (b < l1 && (use_pair && grid->hashed[b]) == pair) ++b;
     const int per_sm = g_bwd_ctas_per_sm > 0 ? g_bwd_ctas_per_sm : g_ctas_per_sm;
     dim3 g((unsigned)ceil_div64(n, kThreads), (unsigned)(b - a));
     if (per_sm > 0) {       // the dense-level kernel strides over the point tiles
@@ -694,5 +897,67 @@ extern "C" int immoco_hashgrid_bwd_taps(const immoco_grid_desc* grid, const immo
   immoco_launch(hashgrid_bwd_taps_kernel, dim3(g), dim3(kThreads), 0, (cudaStream_t)stream, *grid, coords,
                 (const float2*)d_enc, (const uint4*)taps->rows, (float2*)grad_table, n, first, tiles);
   IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- grouped 3-D entry points (see hashgrid_fwd_bundle_kernel) ------------------------------------------------
+static int check_grouped(const immoco_grid_desc* grid, int64_t n_pixels, int32_t n_groups) {
+  if (!grid || n_pixels < 0 || n_groups < 1) return IMMOCO_ERR_BAD_ARG;
+  if (int e = check(grid, n_pixels * n_groups)) return e;
+  if (grid->n_dims != 3 || kThreads != 256) return IMMOCO_ERR_UNSUPPORTED;
+  if (n_groups != 2 && n_groups != 4 && n_groups != 8 && n_groups != 16) return IMMOCO_ERR_UNSUPPORTED;
+  if (grid_has_lut(*grid) && !grid->layout_lut) return IMMOCO_ERR_BAD_ARG;
+  return 0;
+}
+
+extern "C" int immoco_hashgrid_fwd_grouped(const immoco_grid_desc* grid, const float* coords, const float* table,
+                                           float* enc, int64_t n_pixels, int32_t n_groups, void* stream) {
+  if (int e = check_grouped(grid, n_pixels, n_groups)) return e;
+  if (n_pixels == 0) return 0;
+  const int per_item = (kThreads / (2 * n_groups)) * kBundleIters;
+  const int tiles = (int)ceil_div64(n_pixels, per_item);
+  const int64_t items = (int64_t)tiles * grid->n_levels;
+  const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
+  const unsigned g = (unsigned)(items < cap ? items : cap);
+  immoco_launch(hashgrid_fwd_bundle_kernel, dim3(g), dim3(kThreads), 0, (cudaStream_t)stream, *grid, coords,
+                (const float2*)table, (float2*)enc, (int)n_pixels, (int)n_groups, 0, grid->n_levels, tiles);
+  IMMOCO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int immoco_hashgrid_bwd_grouped(const immoco_grid_desc* grid, const float* coords, const float* d_enc,
+                                           float* grad_table, int64_t n_pixels, int32_t n_groups, void* stream) {
+  if (int e = check_grouped(grid, n_pixels, n_groups)) return e;
+  if (n_pixels == 0) return 0;
+  const int64_t n = n_pixels * n_groups;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int per_item = (kThreads / (2 * n_groups)) * kBundleItersBwd;
+  const int tiles = (int)ceil_div64(n_pixels, per_item);
+  const int per_sm = g_bwd_ctas_per_sm > 0 ? g_bwd_ctas_per_sm : g_ctas_per_sm;
+  // consecutive levels of one kind per launch: hashed power-of-two levels -> bundle kernel, the others -> the
+  // run-aggregating kernel (one thread per point)
+  for (int a = 0; a < grid->n_levels;) {
+    auto linear = [&](int l) { return grid->hashed[l] != 0u && (grid->entries[l] & (grid->entries[l] - 1u)) == 0u; };
+    int b = a + 1;
+    const bool lin = linear(a);
+    while (b < grid->n_levels && linear(b) == lin) ++b;
+    if (lin) {
+      const int64_t items = (int64_t)tiles * (b - a);
+      const int64_t cap = per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * per_sm : items;
+      const unsigned gp = (unsigned)(items < cap ? items : cap);
+      immoco_launch(hashgrid_bwd_bundle_kernel, dim3(gp), dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc,
+                    (float2*)grad_table, (int)n_pixels, (int)n_groups, a, b - a, tiles);
+    } else {
+      dim3 gd((unsigned)ceil_div64(n, kThreads), (unsigned)(b - a));
+      if (per_sm > 0) {
+        const unsigned gx = (unsigned)((IMMOCO_NUM_SMS * per_sm + (b - a) - 1) / (b - a));
+        if (gx < gd.x) gd.x = gx;
+      }
+      immoco_launch(hashgrid_bwd_kernel<3>, gd, dim3(kThreads), 0, s, *grid, coords, (const float2*)d_enc,
+                    (float2*)grad_table, (int)n, a);
+    }
+    IMMOCO_LAUNCH_CHECK();
+    a = b;
+  }
   return 0;
 }

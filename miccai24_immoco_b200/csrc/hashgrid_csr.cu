@@ -297,6 +297,7 @@ extern "C" int immoco_hashgrid_csr_build(const immoco_grid_desc* grid, const flo
                                          uint32_t* row_ptr, void* taps, void* workspace, int64_t workspace_bytes,
                                          void* stream) {
   if (int e = check(grid, n_points)) return e;
+  if (grid_has_lut(*grid)) return IMMOCO_ERR_UNSUPPORTED;      // chunk-table layouts: grouped scatter kernels only
   if (!coords || !row_ptr || !taps || !workspace) return IMMOCO_ERR_BAD_ARG;
   if (((uintptr_t)taps & 7) != 0 || ((uintptr_t)workspace & 255) != 0) return IMMOCO_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;

@@ -49,9 +49,10 @@ class GridSpec:
     def n_table_params(self) -> int:
         return self.offsets[-1] * 2
 
-    def desc(self, swizzle: Tuple[int, ...] = ()) -> nat.GridDesc:
+    def desc(self, swizzle: Tuple[int, ...] = (), lut_ptr: int = 0) -> nat.GridDesc:
         """C-ABI descriptor; ``swizzle`` (one word per level, see ``row_swizzle``) selects the physical row
-        layout of the hashed levels -- empty = the reference's own layout."""
+        layout of the hashed levels -- empty = the reference's own layout.  A word ``nat.LAYOUT_LUT`` selects the
+        level's chunk tables of ``linear_layout`` at device address ``lut_ptr`` ((n_levels, 256) uint32)."""
         d = nat.GridDesc()
         d.n_dims = self.n_dims
         d.n_levels = self.n_levels
@@ -63,6 +64,9 @@ class GridSpec:
             d.swizzle[i] = int(swizzle[i]) if swizzle else 0
         for i in range(self.n_levels + 1):
             d.offset[i] = self.offsets[i]
+        d.layout_lut = int(lut_ptr) if lut_ptr else None
+        if any(int(w) == nat.LAYOUT_LUT for w in swizzle) and not lut_ptr:
+            raise ValueError("a LAYOUT_LUT level needs the device address of the layout tables")
         return d
 
     def row_swizzle(self, dim0_values) -> Tuple[int, ...]:
@@ -94,6 +98,68 @@ class GridSpec:
             words.append(word)
         return tuple(words)
 
+    def linear_layout(self, dim0_values) -> np.ndarray:
+        """General linear row layout of the hashed levels for a grid whose FIRST coordinate only takes the few
+        values ``dim0_values`` (one per movement group): a (n_levels, 256) uint32 lookup table, zero rows = keep
+        the reference layout.
+
+        For one (dim-1.., corner) hash H the rows a pixel needs over all groups and both dim-0 corners are
+        H ^ d, d in D = {cell_g, cell_g + 1}: a 'bundle' of 2 M rows whose mutual differences span a small
+        subspace V of the index bits (dimension k <= ~M + 1: the pair masks cell ^ (cell + 1) and the cross-group
+        differences).  A linear bijection S that sends a basis of V to the unit vectors e_0 .. e_{k-1} puts every
+        bundle into one aligned block of 2^k rows -- with the most frequent pair mask on e_0 (both rows of those
+        pairs in one 16-byte slot, one RED.ADD.F32x4) and the basis ordered so that the bundle covers as few
+        128-byte lines (16 rows) as possible: 2 instead of 4 lines at M = 4, 1 instead of 2 at M = 2.  ``row_swizzle``
+        is the special case (Gray code + one exchange) that only aligns the pairs.  S is handed to the kernels as
+        three chunk tables: S(x) = T0[x & 127] ^ T1[(x >> 7) & 63] ^ T2[(x >> 13) & 63] (linearity)."""
+        lut = np.zeros((self.n_levels, 256), dtype=np.uint32)
+        vals = [float(v) for v in dim0_values]
+        if len(vals) < 2:
+            return lut
+        for lvl in range(self.n_levels):
+            n = self.entries[lvl]
+            bits = n.bit_length() - 1
+            if not self.hashed[lvl] or (n & (n - 1)) != 0 or bits > 19 or bits < 8:
+                continue
+            cells = []
+            for u in vals:
+                pos = np.float32(np.float64(np.float32(self.scales[lvl])) * np.float64(np.float32(u)) + 0.5)
+                cells.append(int(np.floor(pos)) & 0xFFFFFFFF)
+            d = [((c & (n - 1)), ((c + 1) & 0xFFFFFFFF) & (n - 1)) for c in cells]
+            masks = [a ^ b for a, b in d]
+            cross = [d[g][0] ^ d[0][0] for g in range(1, len(d))]
+            by_freq = sorted(set(masks), key=lambda m: (-masks.count(m), m))
+            best = None
+            for order in (by_freq + cross, [by_freq[0]] + cross + by_freq[1:], cross + by_freq):
+                basis = _gf2_independent([v for v in order if v])
+                mat = _gf2_layout(basis, bits)
+                img = lambda x: _gf2_apply(mat, x)          # noqa: E731
+                lines = {img(dd ^ d[0][0]) >> 4 for pair in d for dd in pair}
+                merged = sum(1 for m in masks if img(m) == 1)
+                key = (-merged, len(lines))       # the scatter is paced by the reduction count, the gather by lines
+                if best is None or key < best[0]:
+                    best = (key, mat)
+            mat = best[1]
+            for x in range(128):
+                lut[lvl, x] = _gf2_apply(mat, x)
+            for x in range(64):
+                lut[lvl, 128 + x] = _gf2_apply(mat, x << 7)
+                lut[lvl, 192 + x] = _gf2_apply(mat, x << 13)
+        return lut
+
+    def row_permutation_lut(self, lut: np.ndarray) -> np.ndarray:
+        """perm[r] = physical row of logical (reference-layout) row r under ``linear_layout``'s tables."""
+        perm = np.arange(self.n_rows, dtype=np.int64)
+        for lvl in range(self.n_levels):
+            if not lut[lvl].any():
+                continue
+            r = np.arange(self.entries[lvl], dtype=np.int64)
+            t = lut[lvl].astype(np.int64)
+            phys = t[r & 127] ^ t[128 + ((r >> 7) & 63)] ^ t[192 + ((r >> 13) & 63)]
+            assert np.array_equal(np.sort(phys), r), "layout is not a bijection"
+            perm[self.offsets[lvl]: self.offsets[lvl + 1]] = self.offsets[lvl] + phys
+        return perm
+
     def row_permutation(self, swizzle: Tuple[int, ...]) -> np.ndarray:
         """perm[r] = physical row of logical (reference-layout) row r, over the whole table."""
         perm = np.arange(self.n_rows, dtype=np.int64)
@@ -108,6 +174,51 @@ class GridSpec:
             r ^= (x << a) | (x << b)
             perm[self.offsets[lvl]: self.offsets[lvl + 1]] = self.offsets[lvl] + r
         return perm
+
+
+
+def _gf2_independent(vectors):
+    """The vectors (ints = bit vectors) that are linearly independent of their predecessors, in order."""
+    reduced, keep = [], []
+    for v in vectors:
+        x = v
+        for b in reduced:
+            x = min(x, x ^ b)
+        if x:
+            reduced.append(x)
+            reduced.sort(reverse=True)
+            keep.append(v)
+    return keep
+
+
+def _gf2_layout(basis, bits: int):
+    """Columns S(e_j), j < bits, of the linear bijection with S(basis[i]) = e_i; the basis is completed with unit
+    vectors (lowest bits first), which go to the remaining unit vectors in order."""
+    cols = list(basis)
+    for j in range(bits):
+        if len(_gf2_independent(cols + [1 << j])) > len(cols):
+            cols.append(1 << j)
+    assert len(cols) == bits
+    # invert B (columns `cols`: B e_i = cols[i]) by Gauss-Jordan on [B | I], rows as ints
+    rows = [sum(((cols[c] >> r) & 1) << c for c in range(bits)) | (1 << (bits + r)) for r in range(bits)]
+    for c in range(bits):
+        piv = next(r for r in range(c, bits) if (rows[r] >> c) & 1)
+        rows[c], rows[piv] = rows[piv], rows[c]
+        for r in range(bits):
+            if r != c and (rows[r] >> c) & 1:
+                rows[r] ^= rows[c]
+    inv_rows = [rw >> bits for rw in rows]                 # row r of S = B^-1
+    return [sum(((inv_rows[r] >> j) & 1) << r for r in range(bits)) for j in range(bits)]      # columns of S
+
+
+def _gf2_apply(cols, x: int) -> int:
+    out, j = 0, 0
+    while x:
+        if x & 1:
+            out ^= cols[j]
+        x >>= 1
+        j += 1
+    return out
 
 
 def grid_spec(n_dims: int, cfg: dict) -> GridSpec:

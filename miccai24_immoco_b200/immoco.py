@@ -249,6 +249,21 @@ def _row_permutation(grid, swizzle, dev) -> torch.Tensor:
     return _ROW_PERM_CACHE[key]
 
 
+_LAYOUT_CACHE: dict = {}
+
+
+def _linear_layout(grid, m: int, dev):
+    """Chunk tables of ``GridSpec.linear_layout`` for m movement groups on the device, the layout words and the row
+    permutation they imply (one per device, grid and group count; shared by all engines)."""
+    key = (str(dev), grid.n_dims, grid.offsets, grid.hashed, int(m))
+    if key not in _LAYOUT_CACHE:
+        lut = grid.linear_layout(torch.linspace(-1, 1, m).numpy())     # dim-0 values of make_grids: no device sync
+        words = tuple(nat.LAYOUT_LUT if lut[lvl].any() else 0 for lvl in range(grid.n_levels))
+        perm = torch.from_numpy(grid.row_permutation_lut(lut)).to(dev)
+        _LAYOUT_CACHE[key] = (_upload(lut.view(np.int32), dev), words, perm)
+    return _LAYOUT_CACHE[key]
+
+
 _CSR_CACHE: dict = {}
 
 
@@ -382,6 +397,7 @@ def clear_caches() -> None:
     """Drops the per-shape device caches (coordinates, row permutations, tap lists)."""
     _CSR_CACHE.clear()
     _TAPS_CACHE.clear()
+    _LAYOUT_CACHE.clear()
     _ROW_PERM_CACHE.clear()
     _COORD_CACHE.clear()
 
@@ -403,7 +419,7 @@ class FitEngine:
 
     def __init__(self, model: IMMoCo, max_iters: int, row_swizzle: bool = True,
                  deterministic: Optional[bool] = None, fuse_adam: Optional[bool] = None,
-                 compact_image: Optional[bool] = None):
+                 compact_image: Optional[bool] = None, grouped_layout: Optional[bool] = None):
         """``deterministic`` (default: the library-wide ``immoco_get_deterministic()``): bit-reproducible fit --
         hash-grid backward as a row-sorted gather over a tap list built once per shape, MLP weight gradients
         as per-CTA blocks added in CTA order, image cotangent in 64-bit fixed point.  ``fuse_adam`` (default:
@@ -423,7 +439,14 @@ class FitEngine:
         self._swizzle: Tuple[int, ...] = ()
         self._perm: Optional[torch.Tensor] = None
         self._n_mlp_motion = mot.mlp.n_params
-        if row_swizzle and m > 0:
+        # 2 / 4 / 8 / 16 groups on the float-atomic path: general linear layout (chunk tables) + the grouped kernels,
+        # which put the rows of all groups of a pixel corner into one or two 128-byte lines
+        self._lut: Optional[torch.Tensor] = None
+        want_grouped = (m in (2, 4, 8, 16) and not self.deterministic and not lib.immoco_get_fused_scatter()
+                        and (True if grouped_layout is None else bool(grouped_layout)))
+        if row_swizzle and want_grouped:
+            self._lut, self._swizzle, self._perm = _linear_layout(mot.grid, m, dev)
+        elif row_swizzle and m > 0:
             u = torch.linspace(-1, 1, m).numpy()        # dim-0 values of make_grids, known without a device sync
             swz = mot.grid.row_swizzle(u) if u.size <= 64 else ()
             if any(swz):
@@ -458,7 +481,8 @@ class FitEngine:
         self.coords_motion = model.input_grid.contiguous() if m > 0 else torch.zeros((1, 3), **f32)
         f = nat.Fit()
         f.h, f.w, f.m = h, w, m
-        f.grid_image, f.grid_motion = img.grid.desc(), mot.grid.desc(self._swizzle)
+        f.grid_image = img.grid.desc()
+        f.grid_motion = mot.grid.desc(self._swizzle, 0 if self._lut is None else self._lut.data_ptr())
         f.width_image, f.act_image = img.mlp.width, img.mlp.act
         f.width_motion, f.act_motion = mot.mlp.width, mot.mlp.act
         f.n_motion, f.n_image = self.n_motion, self.n_image

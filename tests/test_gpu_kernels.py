@@ -353,6 +353,62 @@ def test_hashgrid_tap_indexed_storage_equals_reference_layout(native_lib, h, w):
                                                enc_tap.data_ptr(), n - 1, s) == nat.ERR_BAD_ARG
 
 
+@pytest.mark.parametrize("m,h,w", [(4, 96, 80), (2, 48, 40), (8, 33, 17), (16, 20, 12), (4, 320, 320)])
+@pytest.mark.parametrize("layout", ["lut", "swizzle", "reference"])
+def test_hashgrid_grouped_kernels_equal_lane_pair_kernels(native_lib, m, h, w, layout):
+    """immoco_hashgrid_fwd_grouped / _bwd_grouped (the 2 M lanes of a bundle = all groups x both dim-0 corners of one
+    pixel) under the general linear layout (chunk tables), the Gray/exchange word and the reference layout: features
+    BIT-identical to the lane-pair kernels on the reference layout, gradients equal after un-permuting."""
+    gs = grid_spec(3, mb.encoding_config)
+    coords = mb.make_grids((m, h, w), "cuda").contiguous()
+    n, p = coords.shape[0], h * w
+    u = torch.linspace(-1, 1, m).numpy()
+    lut_t = None
+    if layout == "lut":
+        lut = gs.linear_layout(u)
+        words = tuple(nat.LAYOUT_LUT if lut[l].any() else 0 for l in range(16))
+        assert sum(1 for x in words if x) == 13
+        perm = torch.from_numpy(gs.row_permutation_lut(lut)).cuda()
+        lut_t = torch.from_numpy(lut.view(np.int32)).cuda()
+        desc = gs.desc(words, lut_t.data_ptr())
+    elif layout == "swizzle":
+        words = gs.row_swizzle(u)
+        perm = torch.from_numpy(gs.row_permutation(words)).cuda()
+        desc = gs.desc(words)
+    else:
+        perm = torch.arange(gs.n_rows, device="cuda")
+        desc = gs.desc()
+    g = torch.Generator().manual_seed(13 + m)
+    table = ((torch.rand(gs.n_rows, 2, generator=g) - 0.5) * 1e-2).cuda()
+    d_enc = torch.randn(16, n, 2, generator=g).cuda()
+    d_enc[:, ::5] = 0.0
+    table_p = torch.empty_like(table)
+    table_p.index_copy_(0, perm, table)
+    ref_desc = gs.desc()
+    s = _s()
+    enc_ref, enc_grp, enc_gen = (torch.empty(16, n, 2, device="cuda") for _ in range(3))
+    grad_ref, grad_grp, grad_gen = (torch.zeros_like(table) for _ in range(3))
+    assert native_lib.immoco_hashgrid_fwd(C.byref(ref_desc), coords.data_ptr(), table.data_ptr(), enc_ref.data_ptr(), n, s) == 0
+    assert native_lib.immoco_hashgrid_bwd(C.byref(ref_desc), coords.data_ptr(), d_enc.data_ptr(), grad_ref.data_ptr(), n, s) == 0
+    assert native_lib.immoco_hashgrid_fwd_grouped(C.byref(desc), coords.data_ptr(), table_p.data_ptr(), enc_grp.data_ptr(), p, m, s) == 0
+    assert native_lib.immoco_hashgrid_bwd_grouped(C.byref(desc), coords.data_ptr(), d_enc.data_ptr(), grad_grp.data_ptr(), p, m, s) == 0
+    # the generic entry points honour the same descriptor (chunk tables: one-thread-per-point kernels)
+    assert native_lib.immoco_hashgrid_fwd(C.byref(desc), coords.data_ptr(), table_p.data_ptr(), enc_gen.data_ptr(), n, s) == 0
+    assert native_lib.immoco_hashgrid_bwd(C.byref(desc), coords.data_ptr(), d_enc.data_ptr(), grad_gen.data_ptr(), n, s) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(enc_grp, enc_ref)
+    assert float((enc_gen - enc_ref).norm() / enc_ref.norm()) < 1e-6
+    assert float((grad_grp[perm] - grad_ref).norm() / grad_ref.norm()) < 1e-6
+    assert float((grad_gen[perm] - grad_ref).norm() / grad_ref.norm()) < 1e-6
+    if layout == "lut":
+        # group counts the bundles cannot hold, and consumers that only know the Gray/exchange word, are refused
+        assert native_lib.immoco_hashgrid_fwd_grouped(C.byref(desc), coords.data_ptr(), table_p.data_ptr(),
+                                                      enc_grp.data_ptr(), p, 5, s) == nat.ERR_UNSUPPORTED
+        row_ptr = torch.empty(gs.n_rows + 1, dtype=torch.int32, device="cuda")
+        assert native_lib.immoco_hashgrid_csr_build(C.byref(desc), coords.data_ptr(), n, row_ptr.data_ptr(),
+                                                    row_ptr.data_ptr(), row_ptr.data_ptr(), 1 << 20, s) == nat.ERR_UNSUPPORTED
+
+
 # ------------------------------------------------------------------------------------------------------------
 # deterministic building blocks (include/immoco_b200.h sections 1b, 2, 7)
 # ------------------------------------------------------------------------------------------------------------

@@ -479,9 +479,46 @@ def test_engine_tap_indexed_image_table_equals_reference_layout(h, w, n_mov):
     assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
     assert np.allclose(out[True][3], out[False][3], rtol=1e-4)
     assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < 1e-3
-    # (Adam's first steps are lr * sign(g): entries whose gradient is atomics-order noise may flip)
-    assert float(((out[True][4] - out[False][4]).abs() > 1e-3).float().mean()) < 5e-3
+    # the motion INR is not touched by the image layout, but its first Adam steps are lr * sign(g): table entries whose
+    # gradient is atomics-order noise flip between ANY two runs (a few per cent of the 14 M entries at 320 x 320)
+    assert float(((out[True][4] - out[False][4]).abs() > 1e-3).float().mean()) < (5e-3 if h * w <= 4096 else 0.1)
     assert torch.equal(out[False][2][dead], p_img[dead])            # ... which is what the dense update does too
+
+
+@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (40, 36, 8)])
+def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
+    """FitEngine with the motion table under the general linear layout + the grouped hash-grid kernels (the default for
+    2 / 4 / 8 / 16 movement groups) vs grouped_layout=False (Gray/exchange word + lane-pair kernels): same first forward
+    bits, same losses and parameters (reference layout) after three steps up to the rounding of float atomics."""
+    case = orc.make_case(h, w, n_mov, 1000)
+    masks, k = case["masks"].to(DEV), case["kspace_motion"]
+    model = mb.IMMoCo(masks)
+    p_img = model.image_inr.params.detach().clone()
+    p_mot = model.motion_inr.params.detach().clone()
+    p_mot[2048:3072] *= 10.0
+    p_mot[3072:] *= 300.0
+    lam = mb.lambda_schedule(10, 1e-2)[:3]
+    assert mb.FitEngine(model, 3, deterministic=False)._lut is not None        # the default at these group counts
+    assert mb.FitEngine(model, 3, deterministic=True)._lut is None
+    out = {}
+    for grouped in (False, True):
+        eng = mb.FitEngine(model, 3, grouped_layout=grouped, deterministic=False)
+        assert (eng._lut is not None) == grouped
+        eng.set_kspace((k / k.abs().max() * 16000).to(DEV))
+        eng.reset(p_img, p_mot)
+        assert torch.equal(eng.motion_params(), p_mot)              # in and out again: exact
+        eng.run(lam, 1e-2, 0, 1)
+        torch.cuda.synchronize()
+        first = (eng.k_out.clone(), eng.loss[0].clone(), eng.disp.clone())
+        eng.run(lam, 1e-2, 1, 3)
+        torch.cuda.synchronize()
+        out[grouped] = first + (eng.motion_params(), eng.loss_trace(lam), eng.image_params())
+    assert torch.equal(out[True][2], out[False][2])                 # displacement field of the first forward: same bits
+    assert rel_l2(out[True][0], out[False][0]) < 1e-6
+    assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
+    assert np.allclose(out[True][4], out[False][4], rtol=1e-4)
+    assert float(((out[True][3] - out[False][3]).abs() > 1e-3).float().mean()) < 1e-3
+    assert float(((out[True][5] - out[False][5]).abs() > 1e-3).float().mean()) < 1e-3
 
 
 def test_deferred_gradient_zeroing_equals_zeroing_in_adam():

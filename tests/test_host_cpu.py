@@ -296,3 +296,40 @@ def test_run_batched_and_deterministic_flags_are_part_of_the_public_surface():
     # positional signature of the reference call is untouched (immoco.py:116)
     names = list(inspect.signature(mb.imcoco_motion_correction).parameters)[:6]
     assert names == ["kspace_corr", "masks", "iters", "learning_rate", "lambda_ge", "debug"]
+
+
+@pytest.mark.parametrize("m", [2, 4, 5, 8, 16])
+def test_linear_row_layout_is_a_bijection_that_packs_the_bundles(m):
+    """encoding.py:GridSpec.linear_layout: per hashed level a linear bijection of the index bits (chunk tables) that puts
+    the 2 M rows one pixel corner needs over all groups into fewer 128-byte lines than one line per group, with the most
+    frequent dim-0 pair in one 16-byte slot."""
+    import miccai24_immoco_b200 as mb
+    from miccai24_immoco_b200.encoding import grid_spec
+    gs = grid_spec(3, mb.encoding_config)
+    u = np.linspace(-1, 1, m)
+    lut = gs.linear_layout(u)
+    perm = gs.row_permutation_lut(lut)
+    assert np.array_equal(np.sort(perm), np.arange(gs.n_rows))
+    lines_total, pairs_in_slot = 0, 0
+    for lvl in range(gs.n_levels):
+        if not gs.hashed[lvl]:
+            assert not lut[lvl].any() and np.array_equal(perm[gs.offsets[lvl]:gs.offsets[lvl + 1]],
+                                                          np.arange(gs.offsets[lvl], gs.offsets[lvl + 1]))
+            continue
+        n = gs.entries[lvl]
+        t = lut[lvl].astype(np.int64)
+        s_of = lambda x: int(t[x & 127] ^ t[128 + ((x >> 7) & 63)] ^ t[192 + ((x >> 13) & 63)])   # noqa: E731
+        rng = np.random.default_rng(lvl)
+        for a, b in rng.integers(0, n, size=(50, 2)):
+            assert s_of(int(a) ^ int(b)) == s_of(int(a)) ^ s_of(int(b))            # linear
+        cells = [int(np.floor(np.float32(np.float64(np.float32(gs.scales[lvl])) * np.float64(np.float32(v)) + 0.5)))
+                 & 0xFFFFFFFF for v in u]
+        d = [(c & (n - 1), (c + 1) & (n - 1)) for c in cells]
+        lines = {s_of(x ^ d[0][0]) >> 4 for pair in d for x in pair}
+        assert len(lines) <= max(1, int(np.ceil(0.75 * m)))
+        lines_total += len(lines)
+        pairs_in_slot += sum(1 for a, b in d if s_of(a ^ b) == 1)
+    n_hashed = sum(gs.hashed)
+    assert lines_total <= 0.6 * m * n_hashed
+    assert pairs_in_slot >= n_hashed * (m // 2) * 0.9 or m == 16
+    assert not gs.linear_layout([0.0]).any()           # a single group: nothing to pack
