@@ -94,8 +94,9 @@ int immoco_hashgrid_bwd_levels(const immoco_grid_desc* grid, const float* coords
  * first coordinate depends on the group only, the other two on the pixel only (make_grids((M, H, W)),
  * src/models/immoco.py:48-53,78-80).  The 2 M lanes of a "bundle" take the M groups x 2 dim-0 corners of one pixel, so
  * one gather / reduction instruction touches every 128-byte line that holds rows of that pixel corner once for ALL
- * groups (with an IMMOCO_LAYOUT_LUT layout: 2 lines instead of 4 at M = 4).  n_groups must be 2, 4, 8 or 16
- * (IMMOCO_ERR_UNSUPPORTED otherwise).  Features bit-identical to immoco_hashgrid_fwd on the same table. */
+ * groups (with an IMMOCO_LAYOUT_LUT layout: 2 lines instead of 4 at M = 4).  2 <= n_groups <= 16
+ * (IMMOCO_ERR_UNSUPPORTED otherwise); a bundle has the next power of two >= 2 M lanes, the surplus ones idle.
+ * Features bit-identical to immoco_hashgrid_fwd on the same table. */
 int immoco_hashgrid_fwd_grouped(const immoco_grid_desc* grid, const float* coords, const float* table, float* enc,
                                 int64_t n_pixels, int32_t n_groups, void* stream);
 int immoco_hashgrid_bwd_grouped(const immoco_grid_desc* grid, const float* coords, const float* d_enc,

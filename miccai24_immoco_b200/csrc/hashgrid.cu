@@ -531,6 +531,13 @@ constexpr int kBundleItersBwd = IMMOCO_HG_BUNDLE_ITERS_BWD;
 #define IMMOCO_HG_BUNDLE_MIN_CTAS 6
 #endif
 
+// lanes of a bundle: the next power of two >= 2 M, at least 4 (the four pixel terms are evaluated by lanes 0..3)
+__host__ __device__ __forceinline__ int bundle_lanes(int m) {
+  int l = 4;
+  while (l < 2 * m) l <<= 1;
+  return l;
+}
+
 struct BundleLevel {
   uint32_t mask, swz, res, entries, hashed;
   bool lin;           // hashed power-of-two level: XOR-linear index + linear layout
@@ -575,9 +582,10 @@ hashgrid_fwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const flo
                            int n_levels, int tiles) {
   __shared__ uint32_t lut_s[256];
   pdl_wait();
-  const int lanes = 2 * M, bundles = kThreads / lanes;
+  const int lanes = bundle_lanes(M), bundles = kThreads / lanes;
   const int lb = threadIdx.x % lanes, bundle = threadIdx.x / lanes;
-  const int grp = lb >> 1, half = lb & 1;
+  const bool active = lb < 2 * M;               // group counts that are no power of two leave the bundle's last lanes idle
+  const int grp = active ? lb >> 1 : 0, half = lb & 1;
   const unsigned lead = (threadIdx.x & 31u) & ~(unsigned)(lanes - 1);
   const size_t n = (size_t)P * M;
   const float t_g = __ldg(coords + (size_t)grp * P * 3);
@@ -614,7 +622,7 @@ hashgrid_fwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const flo
         fr[p][0] = f0;
         bundle_rows(lv, lut_s, q0, s0, c1, c2, lb, lead, row);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[p][c] = ok ? load_row(tab + row[c]) : make_float2(0.f, 0.f);
+        for (int c = 0; c < 4; ++c) v[p][c] = (ok && active) ? load_row(tab + row[c]) : make_float2(0.f, 0.f);
       }
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -627,7 +635,7 @@ hashgrid_fwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const flo
         }
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-        if (pix[p] < P && half == 0) out[pix[p]] = acc;
+        if (pix[p] < P && half == 0 && active) out[pix[p]] = acc;
       }
     }
   }
@@ -640,9 +648,10 @@ hashgrid_bwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const flo
                            int level0, int n_levels, int tiles) {
   __shared__ uint32_t lut_s[256];
   pdl_wait();
-  const int lanes = 2 * M, bundles = kThreads / lanes;
+  const int lanes = bundle_lanes(M), bundles = kThreads / lanes;
   const int lb = threadIdx.x % lanes, bundle = threadIdx.x / lanes;
-  const int grp = lb >> 1, half = lb & 1;
+  const bool active = lb < 2 * M;               // group counts that are no power of two leave the bundle's last lanes idle
+  const int grp = active ? lb >> 1 : 0, half = lb & 1;
   const unsigned lead = (threadIdx.x & 31u) & ~(unsigned)(lanes - 1);
   const size_t n = (size_t)P * M;
   const float t_g = __ldg(coords + (size_t)grp * P * 3);
@@ -667,7 +676,7 @@ hashgrid_bwd_bundle_kernel(const __grid_constant__ immoco_grid_desc g, const flo
 #pragma unroll 2
     for (int it = 0; it < kBundleItersBwd; ++it) {
       const int pix = pix0 + it * bundles + bundle;
-      const bool ok = pix < P;
+      const bool ok = pix < P && active;
       float2 go = make_float2(0.f, 0.f);
       float y = 0.f, x = 0.f;
       if (ok) {
@@ -905,7 +914,7 @@ static int check_grouped(const immoco_grid_desc* grid, int64_t n_pixels, int32_t
   if (!grid || n_pixels < 0 || n_groups < 1) return IMMOCO_ERR_BAD_ARG;
   if (int e = check(grid, n_pixels * n_groups)) return e;
   if (grid->n_dims != 3 || kThreads != 256) return IMMOCO_ERR_UNSUPPORTED;
-  if (n_groups != 2 && n_groups != 4 && n_groups != 8 && n_groups != 16) return IMMOCO_ERR_UNSUPPORTED;
+  if (n_groups < 2 || n_groups > 16) return IMMOCO_ERR_UNSUPPORTED;
   if (grid_has_lut(*grid) && !grid->layout_lut) return IMMOCO_ERR_BAD_ARG;
   return 0;
 }
@@ -914,7 +923,7 @@ extern "C" int immoco_hashgrid_fwd_grouped(const immoco_grid_desc* grid, const f
                                            float* enc, int64_t n_pixels, int32_t n_groups, void* stream) {
   if (int e = check_grouped(grid, n_pixels, n_groups)) return e;
   if (n_pixels == 0) return 0;
-  const int per_item = (kThreads / (2 * n_groups)) * kBundleIters;
+  const int per_item = (kThreads / bundle_lanes(n_groups)) * kBundleIters;
   const int tiles = (int)ceil_div64(n_pixels, per_item);
   const int64_t items = (int64_t)tiles * grid->n_levels;
   const int64_t cap = g_ctas_per_sm > 0 ? (int64_t)IMMOCO_NUM_SMS * g_ctas_per_sm : items;
@@ -931,7 +940,7 @@ extern "C" int immoco_hashgrid_bwd_grouped(const immoco_grid_desc* grid, const f
   if (n_pixels == 0) return 0;
   const int64_t n = n_pixels * n_groups;
   cudaStream_t s = (cudaStream_t)stream;
-  const int per_item = (kThreads / (2 * n_groups)) * kBundleItersBwd;
+  const int per_item = (kThreads / bundle_lanes(n_groups)) * kBundleItersBwd;
   const int tiles = (int)ceil_div64(n_pixels, per_item);
   const int per_sm = g_bwd_ctas_per_sm > 0 ? g_bwd_ctas_per_sm : g_ctas_per_sm;
   // consecutive levels of one kind per launch: hashed power-of-two levels -> bundle kernel, the others -> the

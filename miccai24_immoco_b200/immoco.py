@@ -439,11 +439,13 @@ class FitEngine:
         self._swizzle: Tuple[int, ...] = ()
         self._perm: Optional[torch.Tensor] = None
         self._n_mlp_motion = mot.mlp.n_params
-        # 2 / 4 / 8 / 16 groups on the float-atomic path: general linear layout (chunk tables) + the grouped kernels,
+        # 2 .. 16 groups on the float-atomic path: general linear layout (chunk tables) + the grouped kernels,
         # which put the rows of all groups of a pixel corner into one or two 128-byte lines
         self._lut: Optional[torch.Tensor] = None
-        want_grouped = (m in (2, 4, 8, 16) and not self.deterministic and not lib.immoco_get_fused_scatter()
-                        and (True if grouped_layout is None else bool(grouped_layout)))
+        # (default: power-of-two group counts only -- with 3 or 5 groups a bundle's surplus lanes idle and the kernels
+        # are slower than the lane-pair ones: 640 x 368, n_M = 5: 1395 -> 1554 us per iteration, gpurun_out/r308)
+        want_grouped = (2 <= m <= 16 and not self.deterministic and not lib.immoco_get_fused_scatter()
+                        and (m in (2, 4, 8, 16) if grouped_layout is None else bool(grouped_layout)))
         if row_swizzle and want_grouped:
             self._lut, self._swizzle, self._perm = _linear_layout(mot.grid, m, dev)
         elif row_swizzle and m > 0:

@@ -353,7 +353,7 @@ def test_hashgrid_tap_indexed_storage_equals_reference_layout(native_lib, h, w):
                                                enc_tap.data_ptr(), n - 1, s) == nat.ERR_BAD_ARG
 
 
-@pytest.mark.parametrize("m,h,w", [(4, 96, 80), (2, 48, 40), (8, 33, 17), (16, 20, 12), (4, 320, 320)])
+@pytest.mark.parametrize("m,h,w", [(4, 96, 80), (2, 48, 40), (8, 33, 17), (16, 20, 12), (5, 40, 36), (3, 33, 17), (4, 320, 320)])
 @pytest.mark.parametrize("layout", ["lut", "swizzle", "reference"])
 def test_hashgrid_grouped_kernels_equal_lane_pair_kernels(native_lib, m, h, w, layout):
     """immoco_hashgrid_fwd_grouped / _bwd_grouped (the 2 M lanes of a bundle = all groups x both dim-0 corners of one
@@ -368,6 +368,7 @@ def test_hashgrid_grouped_kernels_equal_lane_pair_kernels(native_lib, m, h, w, l
         lut = gs.linear_layout(u)
         words = tuple(nat.LAYOUT_LUT if lut[l].any() else 0 for l in range(16))
         assert sum(1 for x in words if x) == 13
+        assert np.array_equal(np.sort(gs.row_permutation_lut(lut)), np.arange(gs.n_rows))
         perm = torch.from_numpy(gs.row_permutation_lut(lut)).cuda()
         lut_t = torch.from_numpy(lut.view(np.int32)).cuda()
         desc = gs.desc(words, lut_t.data_ptr())
@@ -402,8 +403,9 @@ def test_hashgrid_grouped_kernels_equal_lane_pair_kernels(native_lib, m, h, w, l
     assert float((grad_gen[perm] - grad_ref).norm() / grad_ref.norm()) < 1e-6
     if layout == "lut":
         # group counts the bundles cannot hold, and consumers that only know the Gray/exchange word, are refused
-        assert native_lib.immoco_hashgrid_fwd_grouped(C.byref(desc), coords.data_ptr(), table_p.data_ptr(),
-                                                      enc_grp.data_ptr(), p, 5, s) == nat.ERR_UNSUPPORTED
+        for bad in (1, 17):
+            assert native_lib.immoco_hashgrid_fwd_grouped(C.byref(desc), coords.data_ptr(), table_p.data_ptr(),
+                                                          enc_grp.data_ptr(), p, bad, s) == nat.ERR_UNSUPPORTED
         row_ptr = torch.empty(gs.n_rows + 1, dtype=torch.int32, device="cuda")
         assert native_lib.immoco_hashgrid_csr_build(C.byref(desc), coords.data_ptr(), n, row_ptr.data_ptr(),
                                                     row_ptr.data_ptr(), row_ptr.data_ptr(), 1 << 20, s) == nat.ERR_UNSUPPORTED

@@ -485,10 +485,10 @@ def test_engine_tap_indexed_image_table_equals_reference_layout(h, w, n_mov):
     assert torch.equal(out[False][2][dead], p_img[dead])            # ... which is what the dense update does too
 
 
-@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (40, 36, 8)])
+@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (40, 36, 8), (64, 46, 5)])
 def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
     """FitEngine with the motion table under the general linear layout + the grouped hash-grid kernels (the default for
-    2 / 4 / 8 / 16 movement groups) vs grouped_layout=False (Gray/exchange word + lane-pair kernels): same first forward
+    2 .. 16 movement groups) vs grouped_layout=False (Gray/exchange word + lane-pair kernels): same first forward
     bits, same losses and parameters (reference layout) after three steps up to the rounding of float atomics."""
     case = orc.make_case(h, w, n_mov, 1000)
     masks, k = case["masks"].to(DEV), case["kspace_motion"]
@@ -498,7 +498,7 @@ def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
     p_mot[2048:3072] *= 10.0
     p_mot[3072:] *= 300.0
     lam = mb.lambda_schedule(10, 1e-2)[:3]
-    assert mb.FitEngine(model, 3, deterministic=False)._lut is not None        # the default at these group counts
+    assert (mb.FitEngine(model, 3, deterministic=False)._lut is not None) == (n_mov in (2, 4, 8, 16))     # the default
     assert mb.FitEngine(model, 3, deterministic=True)._lut is None
     out = {}
     for grouped in (False, True):
@@ -517,8 +517,11 @@ def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
     assert rel_l2(out[True][0], out[False][0]) < 1e-6
     assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
     assert np.allclose(out[True][4], out[False][4], rtol=1e-4)
-    assert float(((out[True][3] - out[False][3]).abs() > 1e-3).float().mean()) < 1e-3
-    assert float(((out[True][5] - out[False][5]).abs() > 1e-3).float().mean()) < 1e-3
+    # Adam's first steps are lr * sign(g): entries whose gradient is atomics-order noise flip between any two runs
+    # (a fraction of a per cent of the 14 M + 11 M entries at 320 x 320, none at the small shapes)
+    tol = 1e-3 if h * w <= 4096 else 2e-2
+    assert float(((out[True][3] - out[False][3]).abs() > 1e-3).float().mean()) < tol
+    assert float(((out[True][5] - out[False][5]).abs() > 1e-3).float().mean()) < tol
 
 
 def test_deferred_gradient_zeroing_equals_zeroing_in_adam():
