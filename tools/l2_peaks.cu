@@ -20,6 +20,13 @@ __device__ __forceinline__ uint32_t mix(uint32_t x) {      // cheap integer hash
 template <int MODE>
 __device__ __forceinline__ uint32_t pick_row(uint32_t item, uint32_t mask) {
   if (MODE == 0) return mix(item) & mask;
+  if (MODE == 3) {
+    // a bundle of the grouped kernels at M = 4: 8 adjacent lanes = 4 groups x 2 dim-0 corners of one
+    // pixel corner under the general linear layout -- two groups with both rows in one 16-byte slot, two whose second
+    // row lies 16 rows further: 8 rows in 2 lines / 5 sectors
+    const uint32_t ofs[8] = {0u, 1u, 2u, 3u, 4u, 20u, 8u, 24u};
+    return (mix(item >> 3) & mask & ~31u) ^ ofs[item & 7u];
+  }
   const uint32_t base = mix(item >> 1) & mask;
   return MODE == 1 ? (base ^ (item & 1u)) : (base ^ ((item & 1u) << 3));
 }
@@ -92,6 +99,7 @@ int main() {
   const float g0 = time_ms([&] { gather_kernel<0, 8><<<grid, 256>>>(table, mask, n_items, sink); }, 5);
   const float g1 = time_ms([&] { gather_kernel<1, 8><<<grid, 256>>>(table, mask, n_items, sink); }, 5);
   const float g2 = time_ms([&] { gather_kernel<2, 8><<<grid, 256>>>(table, mask, n_items, sink); }, 5);
+  const float g3 = time_ms([&] { gather_kernel<3, 8><<<grid, 256>>>(table, mask, n_items, sink); }, 5);
   const float r0 = time_ms([&] { red_kernel<0><<<grid, 256>>>(table, mask, n_items); }, 5);
   const float r1 = time_ms([&] { red_kernel<1><<<grid, 256>>>(table, mask, n_items); }, 5);
   const float r2 = time_ms([&] { red_kernel<2><<<grid, 256>>>(table, mask, n_items); }, 5);
@@ -100,6 +108,7 @@ int main() {
   printf("{\"table_bytes\": %u, \"accesses_per_launch\": %u, \"sms\": %d,\n", rows * 8u, n_items, sms);
   printf(" \"gather_8B_random_Gps\": %.2f, \"gather_8B_pair_same_slot_Gps\": %.2f, \"gather_8B_pair_same_line_Gps\": %.2f,\n",
          n / g0 * 1e-6, n / g1 * 1e-6, n / g2 * 1e-6);
+  printf(" \"gather_8B_bundle8_two_lines_Gps\": %.2f,\n", n / g3 * 1e-6);
   printf(" \"red_f32x2_random_Gps\": %.2f, \"red_f32x2_pair_same_slot_Gps\": %.2f, \"red_f32x2_pair_same_line_Gps\": %.2f,\n",
          n / r0 * 1e-6, n / r1 * 1e-6, n / r2 * 1e-6);
   printf(" \"red_f32x4_merged_pairs_rows_Gps\": %.2f,\n", n / r4 * 1e-6);

@@ -6,9 +6,10 @@ dram__bytes_write.sum, mean over the captured launches) for every profile slot o
 import collections, csv, json, re, subprocess, sys
 
 SLOT_OF = [  # (regex on the kernel name incl. template args, slots it feeds)
-    (r"hashgrid_fwd_pair_kernel<2>", ["hashgrid_fwd_image"]), (r"hashgrid_fwd_pair_kernel<3>", ["hashgrid_fwd_motion"]),
-    (r"hashgrid_bwd_pair_kernel<2>|hashgrid_bwd_kernel<2>", ["hashgrid_bwd_image"]),
-    (r"hashgrid_bwd_pair_kernel<3>|hashgrid_bwd_kernel<3>", ["hashgrid_bwd_motion"]),
+    (r"hashgrid_fwd_pair_kernel<2>|hashgrid_fwd_taps_kernel", ["hashgrid_fwd_image"]),
+    (r"hashgrid_fwd_pair_kernel<3>|hashgrid_fwd_bundle_kernel", ["hashgrid_fwd_motion"]),
+    (r"hashgrid_bwd_pair_kernel<2>|hashgrid_bwd_kernel<2>|hashgrid_bwd_taps_kernel", ["hashgrid_bwd_image"]),
+    (r"hashgrid_bwd_pair_kernel<3>|hashgrid_bwd_kernel<3>|hashgrid_bwd_bundle_kernel", ["hashgrid_bwd_motion"]),
     (r"mlp_fwd_tc_kernel<256", ["mlp_fwd_image"]), (r"mlp_fwd_tc_kernel<64", ["mlp_fwd_motion"]),
     (r"mlp_bwd_tc_kernel<256", ["mlp_bwd_image"]), (r"mlp_bwd_tc64_kernel", ["mlp_bwd_motion"]),
     (r"fft_rows_kernel<0>|fft_rows_kernel<false>", ["fft_rows"]), (r"fft_rows_kernel<1>|fft_rows_kernel<true>", ["fft_rows_adj"]),
@@ -17,7 +18,7 @@ SLOT_OF = [  # (regex on the kernel name incl. template args, slots it feeds)
     (r"colpass_loss_kernel", ["colpass_loss"]), (r"grad_entropy_kernel", ["grad_entropy"]),
     (r"adam_kernel", ["adam_motion", "adam_image"]),
 ]
-N_MOTION, N_IMAGE = 14232576, 11196928
+N_MOTION, N_IMAGE = 14232576, 6230672      # image: MLP block + the live rows of the tap-indexed table at 320 x 320
 
 
 def main(src, dst):
