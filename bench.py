@@ -181,10 +181,12 @@ def algorithmic_bytes(slot: str, p: int, m: int, n_par, t_img: int, t_mot: int) 
 
 # what actually paces each kernel (ncu --set full, profiles/)
 LIMITERS = {
-    "hashgrid_bwd_motion": "L1 wavefronts + L2 atomic throughput (ncu: l1tex 78 %, lts 74 %, DRAM 10 %): 52.4 M 8-byte "
-                           "reductions on hashed rows with no locality across pixels; DRAM traffic equals the algorithmic bytes",
-    "hashgrid_fwd_motion": "L1 wavefronts (ncu: l1tex 75 %, lts 57 %, DRAM 10 %): 52.4 M 8-byte gathers on hashed rows, "
-                           "one 128-byte line per lane pair",
+    "hashgrid_bwd_motion": "SM-side reduction issue, 1.29 cycles per lane and RED (ncu: l1tex 78 %, lts 71 %, DRAM 10 %): 52.4 M "
+                           "8-byte reductions on hashed rows with no locality across pixels, half of the dim-0 pairs merged into "
+                           "one RED.ADD.F32x4; DRAM traffic equals the algorithmic bytes",
+    "hashgrid_fwd_motion": "L1 data stage, two 32-byte sectors per wavefront (ncu: l1tex data-pipe wavefronts 76 %, lts 38 %, "
+                           "DRAM 10 %): 52.4 M 8-byte gathers on hashed rows; the grouped kernels + linear row layout halved "
+                           "the lines and L2 requests per pixel corner (profiles/round2_grouped_kernels.txt)",
     "hashgrid_bwd_image": "L2 atomic throughput", "hashgrid_fwd_image": "L1 wavefronts / L2 gather rate",
     "adam_motion": "HBM (28 B / parameter; the zeroing of the gradients runs as a memset on a third stream)",
     "adam_image": "HBM",
@@ -243,7 +245,11 @@ def roofline_block(nat, ms_sum, n_prof, h, w, m, n_par2, t_img, t_mot, ms_per_it
         with open(os.path.join(ROOT, "profiles", "round2_l2_peaks.json")) as f:
             pk = json.load(f)
         l2 = {"unit": "G table rows / s (one row = 8 bytes = one 32-byte L2 sector)", "source": "profiles/round2_l2_peaks.json"}
-        for slot, taps, key in (("hashgrid_fwd_motion", m * p * 8 * 16, "gather_8B_pair_same_line_Gps"),
+        # the grouped kernels read a pixel corner's rows of ALL groups with adjacent lanes (M = 2, 4, 8, 16): their
+        # reference pattern is the micro-benchmark's 8-lane bundle (8 rows in two lines), not the lane pair
+        fwd_m_key = ("gather_8B_bundle8_two_lines_Gps" if m in (2, 4, 8, 16) and "gather_8B_bundle8_two_lines_Gps" in pk
+                     else "gather_8B_pair_same_line_Gps")
+        for slot, taps, key in (("hashgrid_fwd_motion", m * p * 8 * 16, fwd_m_key),
                                 ("hashgrid_bwd_motion", m * p * 8 * 16, "red_f32x2_pair_same_slot_Gps"),
                                 ("hashgrid_fwd_image", p * 4 * 16, "gather_8B_pair_same_line_Gps"),
                                 ("hashgrid_bwd_image", p * 4 * 16, "red_f32x2_pair_same_slot_Gps")):

@@ -464,7 +464,8 @@ def test_engine_tap_indexed_image_table_equals_reference_layout(h, w, n_mov):
         eng.run(lam, 1e-2, 1, 3)
         torch.cuda.synchronize()
         assert float(eng.state[0].abs().max()) == 0.0               # gradients are clean when a call returns
-        out[compact] = first + (eng.image_params(), eng.loss_trace(lam), eng.motion_params())
+        out[compact] = first + (eng.image_params(), eng.loss_trace(lam), eng.motion_params(), eng.image.clone(),
+                                eng.k_out.clone())
         if compact:
             live = eng._n_mlp_image + 2 * eng._taps.n_active_rows
             assert live < eng.n_image
@@ -478,14 +479,16 @@ def test_engine_tap_indexed_image_table_equals_reference_layout(h, w, n_mov):
     assert rel_l2(out[True][0], out[False][0]) < 1e-6               # the features are bit-identical; the row pass adds atomically
     assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
     assert np.allclose(out[True][3], out[False][3], rtol=1e-4)
-    assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < 1e-3
-    # the motion INR is not touched by the image layout, but its first Adam steps are lr * sign(g): table entries whose
-    # gradient is atomics-order noise flip between ANY two runs (a few per cent of the 14 M entries at 320 x 320)
-    assert float(((out[True][4] - out[False][4]).abs() > 1e-3).float().mean()) < (5e-3 if h * w <= 4096 else 0.1)
+    # after two Adam steps: see the noise floor quoted in test_engine_grouped_motion_layout_equals_lane_pair_layout
+    big = h * w > 4096
+    for key in (5, 6):                                              # image, k-space of the third forward pass
+        assert rel_l2(out[True][key], out[False][key]) < (3e-2 if big else 1e-2)
+    assert float(((out[True][2] - out[False][2]).abs() > 1e-3).float().mean()) < (0.4 if big else 0.02)
+    assert float(((out[True][4] - out[False][4]).abs() > 1e-3).float().mean()) < (0.4 if big else 0.02)
     assert torch.equal(out[False][2][dead], p_img[dead])            # ... which is what the dense update does too
 
 
-@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (40, 36, 8), (64, 46, 5)])
+@pytest.mark.parametrize("h,w,n_mov", [(320, 320, 4), (64, 48, 2), (32, 128, 8), (64, 46, 5)])
 def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
     """FitEngine with the motion table under the general linear layout + the grouped hash-grid kernels (the default for
     2 .. 16 movement groups) vs grouped_layout=False (Gray/exchange word + lane-pair kernels): same first forward
@@ -498,7 +501,9 @@ def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
     p_mot[2048:3072] *= 10.0
     p_mot[3072:] *= 300.0
     lam = mb.lambda_schedule(10, 1e-2)[:3]
-    assert (mb.FitEngine(model, 3, deterministic=False)._lut is not None) == (n_mov in (2, 4, 8, 16))     # the default
+    m = model.num_movements
+    assert m == n_mov                           # (the simulator merges groups on narrow images)
+    assert (mb.FitEngine(model, 3, deterministic=False)._lut is not None) == (m in (2, 4, 8, 16))     # the default
     assert mb.FitEngine(model, 3, deterministic=True)._lut is None
     out = {}
     for grouped in (False, True):
@@ -512,16 +517,22 @@ def test_engine_grouped_motion_layout_equals_lane_pair_layout(h, w, n_mov):
         first = (eng.k_out.clone(), eng.loss[0].clone(), eng.disp.clone())
         eng.run(lam, 1e-2, 1, 3)
         torch.cuda.synchronize()
-        out[grouped] = first + (eng.motion_params(), eng.loss_trace(lam), eng.image_params())
+        out[grouped] = first + (eng.motion_params(), eng.loss_trace(lam), eng.image_params(), eng.disp.clone(),
+                                eng.image.clone(), eng.k_out.clone())
     assert torch.equal(out[True][2], out[False][2])                 # displacement field of the first forward: same bits
     assert rel_l2(out[True][0], out[False][0]) < 1e-6
     assert torch.allclose(out[True][1], out[False][1], rtol=1e-6)
     assert np.allclose(out[True][4], out[False][4], rtol=1e-4)
-    # Adam's first steps are lr * sign(g): entries whose gradient is atomics-order noise flip between any two runs
-    # (a fraction of a per cent of the 14 M + 11 M entries at 320 x 320, none at the small shapes)
-    tol = 1e-3 if h * w <= 4096 else 2e-2
-    assert float(((out[True][3] - out[False][3]).abs() > 1e-3).float().mean()) < tol
-    assert float(((out[True][5] - out[False][5]).abs() > 1e-3).float().mean()) < tol
+    # After two Adam steps: Adam's first steps are lr * sign(g), so entries whose gradient is atomics-order noise (table
+    # rows only background pixels touch) flip between ANY two runs.  Measured noise floor of two runs of the SAME
+    # configuration (tools/layout_noise.py, profiles/round2_layout_noise.txt): 320 x 320: 8-13 % of the motion entries
+    # differ by > 1e-3 and the third forward pass by 2-4e-3 (rel. L2); small shapes: < 1e-5 / < 1e-4.  A wrong storage
+    # permutation scrambles nearly every entry and the forward pass completely.
+    big = h * w > 4100
+    for key in (6, 7, 8):                                           # displacements, image, k-space of the third pass
+        assert rel_l2(out[True][key], out[False][key]) < (3e-2 if big else 1e-2)
+    assert float(((out[True][3] - out[False][3]).abs() > 1e-3).float().mean()) < (0.4 if big else 0.02)
+    assert float(((out[True][5] - out[False][5]).abs() > 1e-3).float().mean()) < (0.4 if big else 0.02)
 
 
 def test_deferred_gradient_zeroing_equals_zeroing_in_adam():
