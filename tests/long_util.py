@@ -33,7 +33,7 @@ def summarize(trace, image_abs, gt_abs):
     # one (oracle and ours alike, 10-25 % of the runs) reports a tail 10-100 x above its own level.
     return {"tail": float(np.percentile(trace[-200:], 10)), "tail_median50": float(np.median(trace[-50:])),
             "last": float(trace[-1]), "max_tail": float(trace[-50:].max()), "spikes": spikes,
-            "psnr": float(met["psnr"]), "ssim": float(met["ssim"])}
+            "psnr": float(met["psnr"]), "ssim": float(met["ssim"]), "rmse": float(met["rmse"])}
 
 
 def run_ours(seed, iters, deterministic):
