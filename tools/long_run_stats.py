@@ -24,7 +24,7 @@ if __name__ == "__main__":
     print(f"[{time.time() - t0:.0f} s]")
     names = ["deterministic", "atomic", "oracle_perturbed"] + [f"oracle_perturbed{j + 1}" for j in range(1, a.perturbed)]
     for mode in names:
-        for key, rel in (("psnr", False), ("ssim", False), ("tail", True), ("tail_median50", True), ("last", True)):
+        for key, rel in (("psnr", False), ("rmse", False), ("ssim", False), ("tail", True), ("tail_median50", True), ("last", True)):
             d = lu.spread(rows, mode, "oracle", key, rel)
             print(f"{mode:17s} vs oracle, {key:13s}{' (relative)' if rel else ''}: median {np.median(d):.4g}  max {d.max():.4g}")
     for name in ["oracle"] + names:
