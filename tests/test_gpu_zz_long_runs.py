@@ -12,10 +12,11 @@ change of the image error by a few 1e-4 of the intensity range is 5 - 13 dB.  A 
 therefore only be statistical, with the oracle's own self-difference, measured in the same run on the same slices, as
 yardstick, and the image error has to be compared on a LINEAR scale:
   * final image error (RMSE of the min-max-normalised central crop against the phantom, src/test/test_immoco.py:74-85
-    -- PSNR = -20 log10 RMSE) and SSIM: median over slices of |ours - oracle| <= max(5e-4, 4 x the pooled median of
+    -- PSNR = -20 log10 RMSE) and SSIM: median over slices of |ours - oracle| <= max(1e-3, 4 x the pooled median of
     the oracle's self-differences, the worst self-difference) / max(0.002, ...); no slice further out than
-    max(2e-3, 4 x the worst self-difference) / max(0.01, ...).  Same-configuration runs differ by up to 9e-4 in RMSE at
-    EVERY error level (the file above); 1e-3 is 0.7 dB on the 38-dB slice, 0.1 % of the intensity range everywhere.
+    max(4e-3, 4 x the worst self-difference) / max(0.01, ...).  Same-configuration runs differ by up to 9e-4 in RMSE at
+    EVERY error level (the file above); 1e-3 is 0.7 dB on the 38-dB slice, 0.1 % of the intensity range everywhere
+    (a wrong kernel leaves errors of 1e-2 ... 1e-1).
     The PSNR differences in dB are printed beside it, not asserted: gpurun r313 / r319 measured medians of 2.3 - 2.6 dB
     and a 12 dB outlier for ours against 0.5 - 0.7 dB / 1.7 - 5.1 dB for the oracle's self-differences in the same
     runs, the layout check above shows the same spread between runs of ONE configuration;
@@ -48,7 +49,7 @@ def test_c2_1000_iterations_against_oracle_distribution():
     rows = lu.compare(range(1000, 1000 + n), iters=1000, n_perturbed=n_pert)
     pert = ["oracle_perturbed"] + [f"oracle_perturbed{j + 1}" for j in range(1, n_pert)]
     for mode in ("deterministic", "atomic"):
-        for key, floor_med, floor_max, rel in (("psnr", None, None, False), ("rmse", 5e-4, 2e-3, False),
+        for key, floor_med, floor_max, rel in (("psnr", None, None, False), ("rmse", 1e-3, 4e-3, False),
                                                ("ssim", 0.002, 0.01, False), ("tail", 1e-3, None, True)):
             ours = lu.spread(rows, mode, "oracle", key, rel)
             self_ = np.concatenate([lu.spread(rows, p, "oracle", key, rel) for p in pert])
