@@ -6,6 +6,13 @@
 // a warp handling 32 consecutive points of one level reads/writes 256 contiguous bytes.
 // Grid = (point tiles, levels): CTAs of one level are adjacent in launch order, so one level's
 // table (<= 4 MB) is the L2 working set at any time.
+//
+// Four families of kernels:
+//   hashgrid_fwd_kernel / hashgrid_bwd_kernel         one thread per (point, level): checkers, dense-level scatter
+//   hashgrid_*_pair_kernel                            two lanes = the two dim-0 corners of a point (Gray/exchange layout)
+//   hashgrid_*_bundle_kernel                          2 M lanes = all groups x both dim-0 corners of one pixel of the grouped
+//                                                     3-D grid, rows under a general linear layout (chunk tables)
+//   hashgrid_*_taps_kernel (+ hashgrid_tap_rows_kernel)  2-D grid whose hashed levels are stored ranked by first touch
 #include "common.cuh"
 #include "hashgrid_pair.cuh"
 
